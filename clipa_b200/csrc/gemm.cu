@@ -1,0 +1,155 @@
+// Host launcher + C ABI for the tcgen05 GEMM family (see gemm_tc.cuh for the kernel).
+#include "gemm_tc.cuh"
+#include "host_common.h"
+
+namespace clipa {
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                       cudaStream_t stream) {
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CLIPA_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          GemmSmem<BN>::kTotal));
+    attr_set[dev] = true;
+  }
+  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, stream>>>(ta, tb, p);
+  CLIPA_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CLIPA_OK;
+}
+
+// Builds tensor maps and derived tiling, then dispatches on (BN, majors, epilogue).
+int gemm_dispatch(GemmParams p, const void* A, long long lda, bool a_mn, const void* B,
+                  long long ldb, bool b_mn, int epi, int max_ctas, cudaStream_t stream) {
+  CLIPA_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, CLIPA_ERR_BAD_ARG, "gemm: M,N,K must be positive (%d,%d,%d)",
+                p.M, p.N, p.K);
+  CLIPA_REQUIRE(A && B, CLIPA_ERR_BAD_ARG, "gemm: null operand");
+  const int BN = (p.N <= 128) ? 128 : 256;
+  p.m_blocks = (p.M + kBM - 1) / kBM;
+  p.n_blocks = (p.N + BN - 1) / BN;
+  p.k_blocks = (p.K + kBK - 1) / kBK;
+  if (p.n_per_chunk <= 0) p.n_per_chunk = 1;
+  p.n_chunks = (p.n_blocks + p.n_per_chunk - 1) / p.n_per_chunk;
+  if (p.split_k < 1) p.split_k = 1;
+  if (p.split_k > p.k_blocks) p.split_k = p.k_blocks;
+  p.kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
+  p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+  p.num_items = p.split_k * p.m_blocks * p.n_chunks;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = encode_tmap_2d_bf16(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, kBK, kBM);
+  else       rc = encode_tmap_2d_bf16(&ta, A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda * 2, 64, kBK);
+  if (rc) return rc;
+  if (!b_mn) rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldb * 2, kBK, BN);
+  else       rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb * 2, 64, kBK);
+  if (rc) return rc;
+
+  int grid = num_sms();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (grid > p.num_items) grid = p.num_items;
+
+#define CLIPA_GEMM_CASE(BN_, AMN_, BMN_, EPI_)                                   \
+  if (BN == BN_ && a_mn == AMN_ && b_mn == BMN_ && epi == EPI_)                  \
+    return launch_gemm<BN_, AMN_, BMN_, EPI_>(ta, tb, p, grid, stream);
+#define CLIPA_GEMM_BOTH_BN(AMN_, BMN_, EPI_) \
+  CLIPA_GEMM_CASE(256, AMN_, BMN_, EPI_) CLIPA_GEMM_CASE(128, AMN_, BMN_, EPI_)
+
+  CLIPA_GEMM_BOTH_BN(false, false, EPI_STORE)
+  CLIPA_GEMM_BOTH_BN(false, true, EPI_STORE)
+  CLIPA_GEMM_BOTH_BN(true, false, EPI_STORE)
+  CLIPA_GEMM_BOTH_BN(true, true, EPI_STORE)
+  CLIPA_GEMM_BOTH_BN(false, false, EPI_BIAS_ACT)
+  CLIPA_GEMM_BOTH_BN(false, true, EPI_DACT)
+  CLIPA_GEMM_BOTH_BN(false, false, EPI_ATOMIC_F32)
+  CLIPA_GEMM_BOTH_BN(false, true, EPI_ATOMIC_F32)
+  CLIPA_GEMM_BOTH_BN(true, false, EPI_ATOMIC_F32)
+  CLIPA_GEMM_BOTH_BN(true, true, EPI_ATOMIC_F32)
+  CLIPA_GEMM_BOTH_BN(false, false, EPI_LSE)
+  CLIPA_GEMM_BOTH_BN(false, false, EPI_SOFTMAX_GRAD)
+#undef CLIPA_GEMM_BOTH_BN
+#undef CLIPA_GEMM_CASE
+  set_error("gemm: unsupported combination (epilogue %d, a_major %d, b_major %d)", epi, (int)a_mn,
+            (int)b_mn);
+  return CLIPA_ERR_UNSUPPORTED;
+}
+
+}  // namespace clipa
+
+using namespace clipa;
+
+extern "C" int clipa_gemm(const clipa_gemm_desc* d, void* stream) {
+  CLIPA_REQUIRE(d != nullptr, CLIPA_ERR_BAD_ARG, "gemm: null descriptor");
+  CLIPA_REQUIRE(d->C != nullptr, CLIPA_ERR_BAD_ARG, "gemm: null output");
+  CLIPA_REQUIRE(d->lda % 8 == 0 && d->ldb % 8 == 0, CLIPA_ERR_BAD_ARG,
+                "gemm: lda/ldb must be multiples of 8 elements (got %lld, %lld)", (long long)d->lda,
+                (long long)d->ldb);
+  const bool c_f32 = d->c_dtype == CLIPA_F32;
+  CLIPA_REQUIRE(d->ldc % (c_f32 ? 4 : 8) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d->C) & 15) == 0,
+                CLIPA_ERR_BAD_ARG, "gemm: C must be 16-byte aligned with ldc %% %d == 0", c_f32 ? 4 : 8);
+  GemmParams p{};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.C = d->C; p.ldc = d->ldc; p.c_f32 = c_f32;
+  p.alpha = d->alpha;
+  p.bias = d->bias; p.bias_f32 = d->bias_dtype == CLIPA_F32;
+  p.residual = static_cast<const __nv_bfloat16*>(d->residual); p.ldr = d->ldr;
+  p.aux = static_cast<__nv_bfloat16*>(d->aux); p.ldaux = d->ldaux;
+  p.act = d->act;
+  p.n_per_chunk = 1;
+  p.split_k = 1;
+  if (d->bias) CLIPA_REQUIRE((reinterpret_cast<uintptr_t>(d->bias) & 15) == 0, CLIPA_ERR_BAD_ARG,
+                             "gemm: bias must be 16-byte aligned");
+  int epi;
+  switch (d->epilogue) {
+    case CLIPA_EPI_STORE:
+      epi = EPI_STORE;
+      if (d->residual)
+        CLIPA_REQUIRE(d->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0,
+                      CLIPA_ERR_BAD_ARG, "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
+      break;
+    case CLIPA_EPI_BIAS_ACT:
+      epi = EPI_BIAS_ACT;
+      CLIPA_REQUIRE(!c_f32 && d->N % 32 == 0, CLIPA_ERR_UNSUPPORTED,
+                    "gemm: BIAS_ACT needs bf16 output and N %% 32 == 0 (N=%d)", d->N);
+      if (d->aux)
+        CLIPA_REQUIRE(d->ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(d->aux) & 15) == 0,
+                      CLIPA_ERR_BAD_ARG, "gemm: aux must be 16-byte aligned with ldaux %% 8 == 0");
+      break;
+    case CLIPA_EPI_DACT:
+      epi = EPI_DACT;
+      CLIPA_REQUIRE(!c_f32 && d->N % 32 == 0 && d->aux != nullptr && d->ldaux % 8 == 0 &&
+                        (reinterpret_cast<uintptr_t>(d->aux) & 15) == 0,
+                    CLIPA_ERR_UNSUPPORTED,
+                    "gemm: DACT needs bf16 output, N %% 32 == 0 and an aligned aux (N=%d)", d->N);
+      break;
+    case CLIPA_EPI_ATOMIC_F32: {
+      epi = EPI_ATOMIC_F32;
+      CLIPA_REQUIRE(c_f32, CLIPA_ERR_UNSUPPORTED, "gemm: ATOMIC_F32 needs an f32 output");
+      int sk = d->split_k;
+      if (sk < 0) {  // auto: aim for ~4 waves of work items, at least 8 k-blocks per item
+        const int BN = (d->N <= 128) ? 128 : 256;
+        const long long tiles = (long long)((d->M + kBM - 1) / kBM) * ((d->N + BN - 1) / BN);
+        const int kb = (d->K + kBK - 1) / kBK;
+        long long want = (4LL * num_sms() + tiles - 1) / tiles;
+        long long cap = kb / 8 > 0 ? kb / 8 : 1;
+        sk = (int)(want < cap ? want : cap);
+        if (sk < 1) sk = 1;
+      }
+      p.split_k = sk;
+      break;
+    }
+    default:
+      set_error("gemm: unknown epilogue %d", d->epilogue);
+      return CLIPA_ERR_BAD_ARG;
+  }
+  if (epi != EPI_ATOMIC_F32)
+    CLIPA_REQUIRE(d->split_k <= 1, CLIPA_ERR_UNSUPPORTED, "gemm: split_k>1 only with ATOMIC_F32");
+  return gemm_dispatch(p, d->A, d->lda, d->a_major == CLIPA_MAJOR_MN, d->B, d->ldb,
+                       d->b_major == CLIPA_MAJOR_MN, epi, d->max_ctas,
+                       static_cast<cudaStream_t>(stream));
+}

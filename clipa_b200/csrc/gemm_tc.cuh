@@ -1,0 +1,487 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] * B[N,K]^T)
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      : MMA issuer     (one elected lane issues tcgen05.mma, accumulators in TMEM)
+//   warps 2..9  : epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+//
+// Tile 128 x BN x 64 (BN = 256 or 128), kStages-deep smem ring, two TMEM accumulator stages so the
+// epilogue of tile i overlaps the MMAs of tile i+1.  Operands may be K-major or MN-major (the
+// transposed view is consumed in place through the UMMA descriptor "major" bits, which is what
+// makes dgrad / wgrad run without materialising any transpose).
+#pragma once
+#include "ptx.cuh"
+
+namespace clipa {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kNumEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kNumEpiWarps;
+
+enum : int {
+  EPI_STORE = 0,
+  EPI_BIAS_ACT = 1,
+  EPI_DACT = 2,
+  EPI_ATOMIC_F32 = 3,
+  EPI_LSE = 4,          // contrastive head: online row log-sum-exp, nothing stored per element
+  EPI_SOFTMAX_GRAD = 5  // contrastive head: Pt = exp(s*acc - lse) - onehot
+};
+
+struct GemmParams {
+  int M, N, K;
+  int m_blocks, n_blocks, k_blocks;
+  int n_per_chunk, n_chunks;  // chunk = consecutive n-blocks handled by one work item
+  int split_k, kb_per_split;
+  int num_items;
+  // epilogue operands
+  void* C;
+  long long ldc;
+  int c_f32;
+  float alpha;
+  const void* bias;
+  int bias_f32;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  __nv_bfloat16* aux;
+  long long ldaux;
+  int act;
+  // contrastive head
+  float scale_log2;  // logit_scale * log2(e)
+  int label_offset;
+  const float* lse;    // [M] natural-log lse (SOFTMAX_GRAD input)
+  float* part_max;     // [n_chunks, M] (LSE)
+  float* part_sum;     // [n_chunks, M]
+  float* diag;         // [M] label logit, natural units
+  float* dscale;       // scalar accumulator (SOFTMAX_GRAD)
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+// ------------------------------------------------------------------------------------------------
+// activation math (fp32)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  if (act == 0) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  if (act == 1) {
+    float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    return 0.5f * x * (1.0f + tanhf(u));
+  }
+  return x / (1.0f + __expf(-1.702f * x));
+}
+__device__ __forceinline__ float act_bwd(float x, int act) {
+  if (act == 0) {
+    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+  }
+  if (act == 1) {
+    float x2 = x * x;
+    float u = 0.7978845608028654f * (x + 0.044715f * x * x2);
+    float t = tanhf(u);
+    float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x2);
+    return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+  }
+  float s = 1.0f / (1.0f + __expf(-1.702f * x));
+  return s * (1.0f + 1.702f * x * (1.0f - s));
+}
+
+__device__ __forceinline__ void load_bias32(const void* bias, int bias_f32, int col0, float (&b)[32]) {
+  if (bias_f32) {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(bias) + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = __ldg(p + i);
+      b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+    }
+  } else {
+    const uint4* p = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(bias) + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 t = __ldg(p + i);
+      b[8 * i] = bf16lo(t.x); b[8 * i + 1] = bf16hi(t.x);
+      b[8 * i + 2] = bf16lo(t.y); b[8 * i + 3] = bf16hi(t.y);
+      b[8 * i + 4] = bf16lo(t.z); b[8 * i + 5] = bf16hi(t.z);
+      b[8 * i + 6] = bf16lo(t.w); b[8 * i + 7] = bf16hi(t.w);
+    }
+  }
+}
+__device__ __forceinline__ float load_bias1(const void* bias, int bias_f32, int col) {
+  return bias_f32 ? __ldg(static_cast<const float*>(bias) + col)
+                  : __bfloat162float(static_cast<const __nv_bfloat16*>(bias)[col]);
+}
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, float (&r)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t = __ldg(q + i);
+    r[8 * i] = bf16lo(t.x); r[8 * i + 1] = bf16hi(t.x);
+    r[8 * i + 2] = bf16lo(t.y); r[8 * i + 3] = bf16hi(t.y);
+    r[8 * i + 4] = bf16lo(t.z); r[8 * i + 5] = bf16hi(t.z);
+    r[8 * i + 6] = bf16lo(t.w); r[8 * i + 7] = bf16hi(t.w);
+  }
+}
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float (&f)[32]) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t;
+    t.x = pack_bf16x2(f[8 * i], f[8 * i + 1]);
+    t.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+    t.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+    t.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+    q[i] = t;
+  }
+}
+__device__ __forceinline__ void store_f32x32(float* p, const float (&f)[32]) {
+  float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+}
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+// Per-thread (= per output row) running state of the contrastive-head LSE epilogue.
+struct LseState {
+  float m;  // running max (log2 domain)
+  float l;  // running sum of 2^(t - m)
+  float d;  // label logit (log2 domain), NaN-free sentinel below
+  int found;
+};
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmParams p) {
+  using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator stages
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBM, BN, A_MN, B_MN);
+
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle needs 1024-byte aligned tiles
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kNumEpiWarps);  // one elected arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int items_mn = p.m_blocks * p.n_chunks;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
+        const int split = w / items_mn;
+        const int r = w - split * items_mn;
+        const int m_blk = r / p.n_chunks;
+        const int chunk = r - m_blk * p.n_chunks;
+        const int n_begin = chunk * p.n_per_chunk;
+        const int n_end = min(p.n_blocks, n_begin + p.n_per_chunk);
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(p.k_blocks, kb_begin + p.kb_per_split);
+        for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
+          for (int kb = kb_begin; kb < kb_end; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * S::kStageBytes;
+            uint8_t* sb = sa + S::kABytes;
+            mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+            if constexpr (!A_MN) {
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
+            } else {
+#pragma unroll
+              for (int a = 0; a < kBM / 64; ++a)
+                tma_load_2d(sa + a * (kBK * 128), &tmap_a, &full_bar[stage], m_blk * kBM + a * 64,
+                            kb * kBK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBK, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / 64; ++a)
+                tma_load_2d(sb + a * (kBK * 128), &tmap_b, &full_bar[stage], n_blk * BN + a * 64,
+                            kb * kBK);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
+        const int split = w / items_mn;
+        const int r = w - split * items_mn;
+        const int m_blk = r / p.n_chunks;
+        const int chunk = r - m_blk * p.n_chunks;
+        const int n_begin = chunk * p.n_per_chunk;
+        const int n_end = min(p.n_blocks, n_begin + p.n_per_chunk);
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(p.k_blocks, kb_begin + p.kb_per_split);
+        for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + acc * BN;
+          for (int kb = kb_begin; kb < kb_end; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+            const uint32_t sb = sa + S::kABytes;
+            // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); k-step = +32 B.
+            // MN-major: 64-element (128 B) MN atoms kBK*128 B apart (LBO), 8-k groups 1024 B apart
+            //           (SBO); k-step (16 k-rows) = +2048 B.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa, kBK * 128, 1024)
+                                     : make_smem_desc_sw128(sa, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb, kBK * 128, 1024)
+                                     : make_smem_desc_sw128(sb, 16, 1024);
+            constexpr uint32_t a_step = (A_MN ? 2048 : 32) >> 4;
+            constexpr uint32_t b_step = (B_MN ? 2048 : 32) >> 4;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              umma_bf16(d_addr, da + static_cast<uint64_t>(k * a_step),
+                        db + static_cast<uint64_t>(k * b_step), kIdesc,
+                        (kb > kb_begin || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue warps =======================
+    const int ew = warp - 2;
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;        // which half of the BN columns
+    constexpr int kColsPerWarp = BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < p.num_items; w += gridDim.x) {
+      const int split = w / items_mn;
+      const int r = w - split * items_mn;
+      const int m_blk = r / p.n_chunks;
+      const int chunk = r - m_blk * p.n_chunks;
+      const int n_begin = chunk * p.n_per_chunk;
+      const int n_end = min(p.n_blocks, n_begin + p.n_per_chunk);
+      const int row = m_blk * kBM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+
+      LseState st;
+      st.m = -INFINITY; st.l = 0.f; st.d = 0.f; st.found = 0;
+      float lse2_row = 0.f;
+      float ds_acc = 0.f;
+      if constexpr (EPI == EPI_SOFTMAX_GRAD) lse2_row = row_ok ? p.lse[row] * 1.4426950408889634f : 0.f;
+      const int label = row + p.label_offset;
+
+      for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < kColsPerWarp / 32; ++c) {
+          const int col_local = half * kColsPerWarp + c * 32;
+          const int col0 = n_blk * BN + col_local;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + acc * BN + col_local + (static_cast<uint32_t>(q * 32) << 16), v);
+          tmem_ld_wait();
+          if (col0 >= p.N) continue;  // warp-uniform
+          const bool full = (col0 + 32 <= p.N);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+
+          if constexpr (EPI == EPI_STORE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+            if (full) {
+              if (p.bias) {
+                float b[32];
+                load_bias32(p.bias, p.bias_f32, col0, b);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] += b[j];
+              }
+              if (row_ok) {
+                if (p.residual) {
+                  float rr[32];
+                  load_bf16x32(p.residual + row * p.ldr + col0, rr);
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) f[j] += rr[j];
+                }
+                if (p.c_f32) store_f32x32(static_cast<float*>(p.C) + row * p.ldc + col0, f);
+                else store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+              }
+            } else if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int col = col0 + j;
+                if (col < p.N) {
+                  float x = f[j];
+                  if (p.bias) x += load_bias1(p.bias, p.bias_f32, col);
+                  if (p.residual) x += __bfloat162float(p.residual[row * p.ldr + col]);
+                  if (p.c_f32) static_cast<float*>(p.C)[row * p.ldc + col] = x;
+                  else static_cast<__nv_bfloat16*>(p.C)[row * p.ldc + col] = __float2bfloat16(x);
+                }
+              }
+            }
+          } else if constexpr (EPI == EPI_BIAS_ACT) {
+            // requires N % 32 == 0 (checked on the host)
+            if (p.bias) {
+              float b[32];
+              load_bias32(p.bias, p.bias_f32, col0, b);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += b[j];
+            }
+            if (row_ok) {
+              if (p.aux) {
+                // the pre-activation is stored in bf16 and the activation is evaluated on the
+                // ROUNDED value, so backward (which re-reads aux) sees the same operand
+                store_bf16x32(p.aux + row * p.ldaux + col0, f);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], p.act);
+              store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+            }
+          } else if constexpr (EPI == EPI_DACT) {
+            if (row_ok) {
+              float a[32];
+              load_bf16x32(p.aux + row * p.ldaux + col0, a);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], p.act);
+              store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+            }
+          } else if constexpr (EPI == EPI_ATOMIC_F32) {
+            if (row_ok) {
+              float* dst = static_cast<float*>(p.C) + row * p.ldc + col0;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  red_add_f32x4(dst + j, p.alpha * f[j], p.alpha * f[j + 1], p.alpha * f[j + 2],
+                                p.alpha * f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) atomicAdd(dst + j, p.alpha * f[j]);
+              }
+            }
+          } else if constexpr (EPI == EPI_LSE) {
+            // t = logit * log2(e); online (max, sum 2^(t-max)) per row
+            float gmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              f[j] = (full || col0 + j < p.N) ? f[j] * p.scale_log2 : -INFINITY;
+              gmax = fmaxf(gmax, f[j]);
+            }
+            const float m_new = fmaxf(st.m, gmax);
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += exp2f(f[j] - m_new);
+            st.l = st.l * exp2f(st.m - m_new) + s;
+            st.m = m_new;
+            if (label >= col0 && label < col0 + 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j == label) st.d = f[j];
+              st.found = 1;
+            }
+          } else if constexpr (EPI == EPI_SOFTMAX_GRAD) {
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float pt = exp2f(f[j] * p.scale_log2 - lse2_row) - ((col0 + j == label) ? 1.f : 0.f);
+                const bool ok = full || (col0 + j < p.N);
+                ds_acc += ok ? pt * f[j] : 0.f;
+                f[j] = pt;
+              }
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
+              if (full) store_bf16x32(dst, f);
+              else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) dst[j] = __float2bfloat16(f[j]);
+              }
+            }
+          }
+        }
+        // all of this warp's TMEM reads for the stage are complete (wait::ld above)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+
+      if constexpr (EPI == EPI_LSE) {
+        if (row_ok) {
+          // two warps (column halves) cover a row: slot = chunk*2 + half
+          const long long slot = (static_cast<long long>(chunk) * 2 + half) * p.M + row;
+          p.part_max[slot] = st.m;
+          p.part_sum[slot] = st.l;
+          if (st.found) p.diag[row] = st.d * 0.69314718055994531f;  // back to natural units
+        }
+      }
+      if constexpr (EPI == EPI_SOFTMAX_GRAD) {
+        float v = ds_acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v != 0.f) atomicAdd(p.dscale, v);
+      }
+    }
+  }
+
+  // teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace clipa

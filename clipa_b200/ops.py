@@ -1,0 +1,165 @@
+"""Tensor-level wrappers: torch tensors in, raw device pointers + sizes out to the C ABI.
+
+torch is used here only for memory (allocation, data_ptr) and the current CUDA stream.
+Every function fails loudly if its input is not a CUDA tensor or the library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_QUICK_GELU, BF16, EPI_ATOMIC_F32, EPI_BIAS_ACT,
+                   EPI_DACT, EPI_STORE, F32, MAJOR_K, MAJOR_MN, GemmDesc, check)
+
+ACT_BY_NAME = {"gelu": ACT_GELU_ERF, "gelu_erf": ACT_GELU_ERF, "none": ACT_GELU_ERF,
+               "gelu_tanh": ACT_GELU_TANH, "tanh": ACT_GELU_TANH, "quick_gelu": ACT_QUICK_GELU}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.ClipaError("clipa_b200 kernels need CUDA tensors (there is no CPU path)")
+    return t.data_ptr()
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise _lib.ClipaError(f"unsupported dtype {t.dtype}")
+
+
+def _mat(t: torch.Tensor):
+    """Returns (ptr, ld, major) for a 2-D bf16 tensor that is row-major or a transposed view."""
+    assert t.dim() == 2 and t.dtype == torch.bfloat16, (t.shape, t.dtype)
+    if t.stride(1) == 1:
+        return _ptr(t), t.stride(0), MAJOR_K
+    if t.stride(0) == 1:
+        return _ptr(t), t.stride(1), MAJOR_MN
+    raise _lib.ClipaError(f"operand strides {t.stride()} are neither row- nor column-major")
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, epilogue: int = EPI_STORE,
+         alpha: float = 1.0, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+         act: int = ACT_GELU_ERF, split_k: int = 0, max_ctas: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(alpha * a[M,K] @ b[N,K]^T).  `a`/`b` may be transposed views."""
+    M, K = a.shape
+    N, Kb = b.shape
+    assert K == Kb, (a.shape, b.shape)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    d = GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.a_major = _mat(a)
+    d.B, d.ldb, d.b_major = _mat(b)
+    d.C, d.ldc, d.c_dtype = _ptr(out), out.stride(0), _dtype_code(out)
+    d.epilogue = epilogue
+    d.alpha = alpha
+    if bias is not None:
+        assert bias.numel() == N and bias.is_contiguous()
+        d.bias, d.bias_dtype = _ptr(bias), _dtype_code(bias)
+    if residual is not None:
+        assert residual.shape == (M, N) and residual.stride(1) == 1 and residual.dtype == torch.bfloat16
+        d.residual, d.ldr = _ptr(residual), residual.stride(0)
+    if aux is not None:
+        assert aux.shape == (M, N) and aux.stride(1) == 1 and aux.dtype == torch.bfloat16
+        d.aux, d.ldaux = _ptr(aux), aux.stride(0)
+    d.act = act
+    d.split_k = split_k
+    d.max_ctas = max_ctas
+    check(_lib.lib().clipa_gemm(C.byref(d), _stream()), "clipa_gemm")
+    return out
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+                  save_stats: bool = True):
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    D = x.shape[-1]
+    rows = x.numel() // D
+    y = torch.empty_like(x)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    check(_lib.lib().clipa_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean),
+                                         _ptr(rstd), rows, D, eps, _stream()), "clipa_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres, dgamma, dbeta):
+    """Returns dx = dres + LN'(dy); accumulates into dgamma/dbeta (fp32)."""
+    D = x.shape[-1]
+    rows = x.numel() // D
+    assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
+    dx = torch.empty_like(x)
+    check(_lib.lib().clipa_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd),
+                                         _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), rows, D,
+                                         _stream()), "clipa_layernorm_bwd")
+    return dx
+
+
+def attention_fwd(qkv: torch.Tensor, batch: int, L: int, heads: int, causal: bool):
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
+    D3 = qkv.shape[-1]
+    D = D3 // 3
+    hd = D // heads
+    out = torch.empty(batch * L, D, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(batch, heads, L, dtype=torch.float32, device=qkv.device)
+    check(_lib.lib().clipa_attention_fwd(_ptr(qkv), _ptr(out), _ptr(lse), batch, L, heads, hd,
+                                         int(causal), _stream()), "clipa_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, batch: int, L: int, heads: int, causal: bool):
+    D = out.shape[-1]
+    hd = D // heads
+    assert dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    check(_lib.lib().clipa_attention_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
+                                         batch, L, heads, hd, int(causal), _stream()),
+          "clipa_attention_bwd")
+    return dqkv
+
+
+def colsum_accum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16
+    assert out.dtype == torch.float32 and out.numel() == x.shape[1]
+    check(_lib.lib().clipa_colsum_accum(_ptr(x), x.stride(0), _ptr(out), x.shape[0], x.shape[1],
+                                        _stream()), "clipa_colsum_accum")
+    return out
+
+
+def clip_lse(a: torch.Tensor, b_all: torch.Tensor, scale: float, label_offset: int):
+    """Row log-sum-exp and label logit of scale * a @ b_all^T, logits never materialised."""
+    assert a.dtype == torch.bfloat16 and b_all.dtype == torch.bfloat16
+    assert a.is_contiguous() and b_all.is_contiguous()
+    bl, E = a.shape
+    bg = b_all.shape[0]
+    nws = _lib.lib().clipa_clip_lse_workspace(bl, bg)
+    ws = torch.empty(nws, dtype=torch.float32, device=a.device)
+    lse = torch.empty(bl, dtype=torch.float32, device=a.device)
+    diag = torch.empty(bl, dtype=torch.float32, device=a.device)
+    check(_lib.lib().clipa_clip_lse(_ptr(a), _ptr(b_all), bl, bg, E, scale, label_offset, _ptr(lse),
+                                    _ptr(diag), _ptr(ws), _stream()), "clipa_clip_lse")
+    return lse, diag
+
+
+def clip_softmax_grad(a, b_all, scale: float, label_offset: int, lse: torch.Tensor,
+                      dscale_partial: torch.Tensor):
+    bl, E = a.shape
+    bg = b_all.shape[0]
+    pt = torch.empty(bl, bg, dtype=torch.bfloat16, device=a.device)
+    check(_lib.lib().clipa_clip_softmax_grad(_ptr(a), _ptr(b_all), bl, bg, E, scale, label_offset,
+                                             _ptr(lse), _ptr(pt), pt.stride(0), _ptr(dscale_partial),
+                                             _stream()), "clipa_clip_softmax_grad")
+    return pt

@@ -1,0 +1,140 @@
+/*
+ * clipa_b200 — C ABI of the B200 (sm_100a) kernels behind the CLIPA training-step hot path.
+ *
+ * The reference (UCSC-VLAA/CLIPA, clipa_torch/open_clip) has no FFI: its hot path is Python that
+ * calls torch ops.  Each entry point below replaces the torch call sites named beside it
+ * (paths relative to /root/reference/clipa_torch).  The Python host (clipa_b200/open_clip/*)
+ * binds these with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `h_`; the library never
+ *     allocates, frees or retains caller memory (workspaces are passed in);
+ *   - `stream` is a cudaStream_t (passed as void*); all work is enqueued on it, nothing syncs;
+ *   - return value: 0 = ok, <0 = error (see clipa_status); clipa_last_error() gives a message
+ *     for the calling thread;
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS;
+ *   - bf16 = __nv_bfloat16 bit pattern (uint16_t), f32 = IEEE float.
+ */
+#ifndef CLIPA_B200_H_
+#define CLIPA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLIPA_B200_ABI_VERSION 1
+
+typedef enum clipa_status {
+  CLIPA_OK = 0,
+  CLIPA_ERR_BAD_ARG = -1,     /* null pointer, non-positive dim, misaligned ld/pointer            */
+  CLIPA_ERR_UNSUPPORTED = -2, /* shape/dtype outside what the sm_100a kernels implement           */
+  CLIPA_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed (message has the CUDA string)  */
+  CLIPA_ERR_NO_DEVICE = -4    /* no sm_100 device / driver entry point unavailable                */
+} clipa_status;
+
+typedef enum clipa_dtype { CLIPA_BF16 = 0, CLIPA_F32 = 1 } clipa_dtype;
+
+/* Storage order of a GEMM operand.  A is logically [M,K], B is logically [N,K]; C = A * B^T.
+ *   CLIPA_MAJOR_K : element (r,k) at ptr[r*ld + k]   (torch `x @ W.T` with W [out,in])
+ *   CLIPA_MAJOR_MN: element (r,k) at ptr[k*ld + r]   (the transposed view, read in place) */
+typedef enum clipa_major { CLIPA_MAJOR_K = 0, CLIPA_MAJOR_MN = 1 } clipa_major;
+
+typedef enum clipa_act {
+  CLIPA_ACT_GELU_ERF = 0,  /* nn.GELU(approximate='none')  open_clip/model.py:128-129 */
+  CLIPA_ACT_GELU_TANH = 1, /* nn.GELU(approximate='tanh')  (BigVision configs)         */
+  CLIPA_ACT_QUICK_GELU = 2 /* x*sigmoid(1.702x)            open_clip/transformer.py:37-40 */
+} clipa_act;
+
+typedef enum clipa_epilogue {
+  /* C = alpha*acc (+bias[n]) (+residual[m,n]); C bf16 or f32 */
+  CLIPA_EPI_STORE = 0,
+  /* f = acc + bias; C = act(f) (bf16); if aux != NULL also writes f (bf16) to aux */
+  CLIPA_EPI_BIAS_ACT = 1,
+  /* C = acc * act'(aux[m,n])  (bf16), aux = saved pre-activation */
+  CLIPA_EPI_DACT = 2,
+  /* C (f32) += alpha*acc with red.global.add (split-K capable; caller zero-fills or accumulates) */
+  CLIPA_EPI_ATOMIC_F32 = 3
+} clipa_epilogue;
+
+typedef struct clipa_gemm_desc {
+  int32_t M, N, K;
+  const void* A; int64_t lda; int32_t a_major; /* bf16 */
+  const void* B; int64_t ldb; int32_t b_major; /* bf16 */
+  void* C;       int64_t ldc; int32_t c_dtype; /* clipa_dtype */
+  int32_t epilogue;                            /* clipa_epilogue */
+  float alpha;
+  const void* bias; int32_t bias_dtype;        /* [N] or NULL */
+  const void* residual; int64_t ldr;           /* bf16 [M,N] or NULL (STORE only) */
+  void* aux; int64_t ldaux;                    /* bf16 [M,N] (see epilogue) */
+  int32_t act;                                 /* clipa_act */
+  int32_t split_k;                             /* 0/1 = none; >1 only with ATOMIC_F32; -1 = auto */
+  int32_t max_ctas;                            /* 0 = one persistent CTA per SM */
+} clipa_gemm_desc;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int clipa_abi_version(void);
+const char* clipa_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py: gpu_launches). */
+int64_t clipa_launch_count(void);
+
+/* ---- dense GEMM family (tcgen05.mma, TMA-fed, TMEM accumulators) ---------------------------
+ * Replaces every F.linear / `@` on the path:
+ *   MultiheadAttention in/out projection  open_clip/transformer.py:209,234-236
+ *   mlp.c_fc / mlp.c_proj                 open_clip/transformer.py:216-220,249
+ *   `pooled @ self.proj`, `x @ self.text_projection`  transformer.py:529, model.py:254-260
+ * and their autograd backward (dgrad: B MN-major; wgrad: A and B MN-major, split-K atomic). */
+int clipa_gemm(const clipa_gemm_desc* desc, void* stream);
+
+/* ---- LayerNorm ------------------------------------------------------------------------------
+ * F.layer_norm via LayerNorm/LayerNormFp32 (open_clip/transformer.py:19-34): fp32 statistics,
+ * eps inside the sqrt, affine.  x,y bf16 [rows, D] contiguous; gamma/beta f32 [D];
+ * mean/rstd f32 [rows] are saved for backward (may be NULL in fwd). */
+int clipa_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,
+                        float* rstd, int64_t rows, int32_t D, float eps, void* stream);
+/* dx = (dres ? dres : 0) + LN'(dy); dgamma/dbeta (f32 [D]) are ACCUMULATED (+=). */
+int clipa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
+                        const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                        int64_t rows, int32_t D, void* stream);
+
+/* ---- multi-head self-attention core ---------------------------------------------------------
+ * The SDPA inside nn.MultiheadAttention(need_weights=False) (open_clip/transformer.py:234-236):
+ * O = softmax(Q K^T / sqrt(hd) [+ causal mask]) V, per (sample, head).
+ * qkv bf16 [batch*L, 3*D] (the packed in-projection output: columns [0,D)=Q, [D,2D)=K, [2D,3D)=V,
+ * head h at columns h*hd..), out bf16 [batch*L, D]; lse f32 [batch, heads, L] (natural-log
+ * sum-exp of the scaled scores, saved for backward).  causal != 0 reproduces the text tower's
+ * additive -inf upper-triangular mask (open_clip/transformer.py:618-624). */
+int clipa_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t L,
+                        int32_t heads, int32_t head_dim, int32_t causal, void* stream);
+int clipa_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                        void* dqkv, int32_t batch, int32_t L, int32_t heads, int32_t head_dim,
+                        int32_t causal, void* stream);
+
+/* ---- column sums (bias gradients): out[n] += sum_m x[m,n]; x bf16 [rows, N], out f32 -------- */
+int clipa_colsum_accum(const void* x, int64_t ldx, float* out, int64_t rows, int32_t N,
+                       void* stream);
+
+/* ---- contrastive head -------------------------------------------------------------------------
+ * ClipLoss.forward (open_clip/loss.py:128-157) with local_loss semantics: the caller passes the
+ * LOCAL rows `a` [B_local, E] and the GATHERED other modality `b_all` [B_global, E] (bf16,
+ * L2-normalised); logits = scale * a @ b_all^T are never materialised:
+ *   clipa_clip_lse        : per-row log-sum-exp and the label logit (label = row + label_offset)
+ *                           -> lse[B_local], diag[B_local] (f32, natural log domain)
+ *                           workspace: f32 [2 * n_chunks * B_local], n_chunks from
+ *                           clipa_clip_lse_workspace().
+ *   clipa_clip_softmax_grad: Pt[i,j] = exp(scale*a_i.b_j - lse_i) - [j == i+label_offset] (bf16
+ *                           [B_local, B_global]) and dscale_partial += sum_ij Pt[i,j]*(a_i.b_j).
+ * The caller (ClipLoss autograd function) turns these into loss, d a, d b_all via clipa_gemm. */
+int64_t clipa_clip_lse_workspace(int32_t b_local, int32_t b_global);
+int clipa_clip_lse(const void* a, const void* b_all, int32_t b_local, int32_t b_global, int32_t E,
+                   float scale, int32_t label_offset, float* lse, float* diag, float* workspace,
+                   void* stream);
+int clipa_clip_softmax_grad(const void* a, const void* b_all, int32_t b_local, int32_t b_global,
+                            int32_t E, float scale, int32_t label_offset, const float* lse,
+                            void* pt, int64_t ldpt, float* dscale_partial, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPA_B200_H_ */
