@@ -177,6 +177,50 @@ def group_loss():
         report(f"clip_softmax_grad dscale bl{bl} bg{bg}", ds, (p_ref * logits / scale).sum().reshape(1), 2e-3)
 
 
+def group_attn():
+    import math
+    for (B, L, H, hd, causal) in [(3, 82, 16, 64, False), (5, 16, 12, 64, True), (2, 37, 16, 80, False),
+                                  (2, 257, 4, 64, False), (4, 8, 16, 64, True), (2, 65, 12, 64, False),
+                                  (3, 32, 12, 64, True), (2, 100, 2, 64, True)]:
+        D = H * hd
+        qkv = mk((B * L, 3 * D))
+        out, lse = ops.attention_fwd(qkv, B, L, H, causal)
+        x = qkv.float().reshape(B, L, 3, H, hd).requires_grad_(True)
+        q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+        s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+        if causal:
+            s = s + torch.full((L, L), float("-inf"), device=dev).triu(1)
+        ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * L, D)
+        tag = f"B{B} L{L} H{H} hd{hd} causal{int(causal)}"
+        report(f"attn_fwd out {tag}", out, ref, 2e-2)
+        report(f"attn_fwd lse {tag}", lse, torch.logsumexp(s, -1), 1e-2)
+        dout = mk((B * L, D))
+        ref.backward(dout.float())
+        dqkv = ops.attention_bwd(qkv, out, dout, lse, B, L, H, causal)
+        gref = x.grad.reshape(B * L, 3 * D)
+        report(f"attn_bwd dq {tag}", dqkv[:, :D], gref[:, :D], 3e-2)
+        report(f"attn_bwd dk {tag}", dqkv[:, D:2 * D], gref[:, D:2 * D], 3e-2)
+        report(f"attn_bwd dv {tag}", dqkv[:, 2 * D:], gref[:, 2 * D:], 3e-2)
+    # timing at the config-3 shape (per layer): B=1024 x 16 heads, L=82
+    B, L, H, hd = 1024, 82, 16, 64
+    qkv = mk((B * L, 3 * H * hd))
+    for _ in range(3):
+        out, lse = ops.attention_fwd(qkv, B, L, H, False)
+    dout = mk((B * L, H * hd))
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(10):
+        out, lse = ops.attention_fwd(qkv, B, L, H, False)
+    e1.record()
+    for _ in range(10):
+        ops.attention_bwd(qkv, out, dout, lse, B, L, H, False)
+    e2.record()
+    torch.cuda.synchronize()
+    fb = B * L * H * hd * 2 * 4
+    print(f"PERF attn B{B} L{L}: fwd {e0.elapsed_time(e1) / 10:.3f} ms ({fb / (e0.elapsed_time(e1) / 10) / 1e6:.0f} GB/s), "
+          f"bwd {e1.elapsed_time(e2) / 10:.3f} ms ({fb * 2 / (e1.elapsed_time(e2) / 10) / 1e6:.0f} GB/s)", flush=True)
+
+
 def group_gemm_perf():
     for (M, N, K) in [(8192, 8192, 8192), (82 * 1024, 3072, 1024), (82 * 1024, 4096, 1024),
                       (82 * 1024, 1024, 4096), (82 * 1024, 1024, 1024)]:

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out/probe
 export PYTHONPATH="$PWD:$PYTHONPATH"
 groups="$@"
-[ -z "$groups" ] && groups="gemm_kk gemm_tails gemm_kmn gemm_mnmn gemm_epi ln loss gemm_perf"
+[ -z "$groups" ] && groups="gemm_kk gemm_tails gemm_kmn gemm_mnmn gemm_epi ln loss attn gemm_perf"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/probe/gpu.txt 2>&1
 for g in $groups; do
   echo "=== $g ===" | tee gpurun_out/probe/$g.log
