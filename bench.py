@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the CLIPA training-step hot path (BASELINE.json metric: image-text pairs/sec at
+ViT-L/14, global batch 32k, on 1/2/4/8 B200).
+
+  python bench.py --gpus 1 --steps K --warmup W                  (single GPU)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...                           (CPU arm: the oracle port)
+
+A "step" is one full optimizer step at the named global batch: H2D/preprocess (e2e only) ->
+towers forward -> all-gather -> fused contrastive head -> backward -> gradient all-reduce ->
+AdamW -> logit-scale clamp.  Global batch is FIXED as N grows ("strong" scaling): each rank
+processes global/N pairs in micro-batches of <= --micro-batch (GradCache schedule when more than
+one micro-batch is needed, as in the reference's accum_freq path).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# model, image px, pos-embed, global batch, algorithmic fwd+bwd GFLOP per pair
+WORKLOADS = {
+    "vitl14_i81_t16_gb32k": dict(model="ViT-L-14-CL16", image=126, pos="sin_cos_2d", global_batch=32768,
+                                 gflop_per_pair=159.35, baseline_config="configs[2]"),
+    "vitb16_i64_t16_gb16k": dict(model="ViT-B-16-CL16", image=128, pos="sin_cos_2d", global_batch=16384,
+                                 gflop_per_pair=37.57, baseline_config="configs[1]"),
+    "vitl14_i256_t32_gb16k": dict(model="ViT-L-14-CL32", image=224, pos="learnable", global_batch=16384,
+                                  gflop_per_pair=502.65, baseline_config="configs[3]"),
+    "vith14_i36_t8_gb64k": dict(model="ViT-H-14-CL8-SyntaxMask-GAP", image=84, pos="sin_cos_2d",
+                                global_batch=65536, gflop_per_pair=155.84, baseline_config="configs[4]"),
+    # small plumbing case for smoke runs of this script
+    "vitb32_i36_t16_gb256": dict(model="ViT-B-32-CL16", image=192, pos="sin_cos_2d", global_batch=256,
+                                 gflop_per_pair=23.16, baseline_config="configs[0] shape, batch 256"),
+}
+METRIC = "image-text pairs/sec at ViT-L/14, global batch 32k, 1/2/4/8 B200"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (bounded sample of the same workload)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(wl, batch):
+    import torch
+    from clipa_b200.open_clip import get_model_config
+    from oracle import clip_oracle as O
+    from oracle.weights import make_inputs, make_state_dict
+    O.USE_FUSED = True   # same fused CPU primitives the reference calls (see oracle/clip_oracle.py)
+    cfg = get_model_config(wl["model"])
+    sd = make_state_dict(cfg, 0, image_size=wl["image"], pos_embed=wl["pos"])
+    for v in sd.values():
+        v.requires_grad_(True)
+    images, text = make_inputs(cfg, batch, 1, image_size=wl["image"])
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        loss = O.train_step_loss(images, text, sd, cfg)
+        loss.backward()
+        return float(loss.detach())
+    return step
+
+
+def cpu_baseline(wl, budget_s=20.0, batch=8):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(wl, batch)
+    step()  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        step(); n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 10:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": batch / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"oracle (oracle/clip_oracle.py) fwd+loss+bwd of {wl['model']} @{wl['image']}px, "
+                      f"batch {batch}, {n} steps after 1 warm-up, fp32, torch CPU threads={cores}"}
+
+
+def run_reference_arm(args, wl, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = args.cpu_batch
+    step = cpu_step_fn(wl, batch)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = batch / dt
+    sample = (f"each step = oracle port of the reference path, {wl['model']} @{wl['image']}px, batch {batch} "
+              f"(bounded sample of the {wl['global_batch']}-pair step), fp32, torch CPU threads={cores}")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "model": wl["model"], "global_batch": wl["global_batch"], "cpu_batch": batch},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="vitl14_i81_t16_gb32k", choices=list(WORKLOADS))
+    ap.add_argument("--global-batch", type=int, default=None)
+    ap.add_argument("--micro-batch", type=int, default=4096)
+    ap.add_argument("--precision", default="amp_bf16", choices=["amp_bf16", "bf16"])
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    name = args.workload
+    wl = dict(WORKLOADS[name])
+    if args.global_batch:
+        wl["global_batch"] = args.global_batch
+    if args.impl == "reference":
+        run_reference_arm(args, wl, name)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from clipa_b200 import _lib, open_clip, ops
+    from clipa_b200.training import TrainStep
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    gb = wl["global_batch"]
+    assert gb % world == 0
+    bl = gb // world
+    torch.manual_seed(0)
+    model, _, _ = open_clip.create_model_and_transforms(wl["model"], precision=args.precision, device=dev,
+                                                        force_image_size=wl["image"], pos_embed=wl["pos"],
+                                                        output_dict=True)
+    if world > 1:  # identical replicas (DDP's initial broadcast, training/main.py:299)
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    model.train()
+    trainer = TrainStep(model, rank=rank, world_size=world, micro_batch=args.micro_batch)
+    ctx = model.context_length
+    vocab = model.vocab_size
+    g = torch.Generator().manual_seed(1 + rank)
+    # host buffers in pinned memory: uint8 images (--to-float-on-device recipe) and int64 token ids
+    h_images = torch.randint(0, 256, (bl, 3, wl["image"], wl["image"]), generator=g, dtype=torch.uint8).pin_memory()
+    h_text = torch.randint(1, vocab - 1, (bl, ctx), generator=g, dtype=torch.int64)
+    h_text[:, -1] = vocab - 1
+    h_text = h_text.pin_memory()
+    d_images = trainer.preprocess(h_images)      # resident, already normalised bf16
+    d_text = h_text.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        n0 = _lib.launch_count()
+        if profile:
+            ops.PROFILER = ops.GemmProfiler()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        barrier()
+        prof, ops.PROFILER = ops.PROFILER, None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop() if rank == 0 else None
+        return ms.item() / steps, _lib.launch_count() - n0, clocks, prof, last
+
+    # ---- device-resident throughput (`value`) ----
+    ms_step, launches, clocks, prof, last_loss = timed(lambda: trainer.step(d_images, d_text), args.steps,
+                                                       args.warmup, profile=True)
+    value = gb / (ms_step * 1e-3)
+    gemm_tflops, gemm_ms, gemm_calls = prof.summary()
+    gemm_stats = torch.tensor([gemm_ms, float(gemm_calls)], device=dev)
+
+    # ---- end-to-end through the public step with HOST buffers (`e2e`) ----
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            loss = trainer.step(h_images, h_text)       # pinned host -> device inside the step
+            return loss.item()                           # device -> host read of the result
+        ms_e2e, _, _, _, _ = timed(e2e_step, max(2, args.steps // 2), 1)
+        e2e = {"value": gb / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": (h_images.numel() + h_text.numel() * 8) * world,
+               "d2h_bytes_per_step": 4 * world,
+               "steps": max(2, args.steps // 2), "warmup": 1,
+               "note": "h2d = uint8 images + int64 token ids from pinned memory, all ranks; d2h = loss scalar"}
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        peak = pk["bf16_tflops_sustained"]
+        per_gpu_pairs = value / world
+        out = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": name, "baseline_config": wl["baseline_config"], "model": wl["model"],
+                       "image_px": wl["image"], "image_tokens_incl_cls": model.visual.positional_embedding.shape[0],
+                       "text_tokens": ctx, "global_batch": gb, "per_gpu_batch": bl,
+                       "micro_batch": min(bl, args.micro_batch),
+                       "schedule": "plain fwd/bwd" if bl <= args.micro_batch else "GradCache (extra no-grad forward)",
+                       "parallelism": f"dp{world}", "precision": args.precision,
+                       "optimizer": "AdamW (torch fused) inside the timed step", "l2": "inputs_exceed_L2",
+                       "loss_last": float(last_loss),
+                       "algorithmic_gflop_per_pair": wl["gflop_per_pair"],
+                       "model_flops_utilization": per_gpu_pairs * wl["gflop_per_pair"] / (peak * 1e3)},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all epilogues/majors)",
+                         "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
+                         "traffic": None, "peak_source": pk_src + ", sustained figure (kernel timed inside a long step)",
+                         "gemm_launches_timed": gemm_calls, "gemm_ms_per_step": gemm_ms / args.steps,
+                         "gemm_share_of_step": gemm_ms / args.steps / ms_step},
+        }
+        if e2e:
+            out["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(wl, batch=args.cpu_batch)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

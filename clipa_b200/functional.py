@@ -1,0 +1,243 @@
+"""torch.autograd.Functions whose forward AND backward are the sm_100a kernels (via clipa_b200.ops).
+
+Activations are bf16, token-major: a tower holds its residual stream as one [batch*L, D] matrix
+(sample-major rows), so every projection is a single GEMM over all tokens and the attention
+kernel finds a head's Q/K/V as strided 128-byte row segments of the packed QKV matrix.
+
+Parameter handling: "compute" copies of matmul weights are bf16.  In pure-bf16 precision the
+parameters already are bf16; with fp32 master weights (amp_bf16 / fp32 flags) a bf16 shadow is
+refreshed whenever the parameter's version counter changes.  Weight gradients are produced in fp32
+by the split-K wgrad GEMM and returned in the parameter's dtype.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import EPI_ATOMIC_F32, EPI_BIAS_ACT, EPI_DACT, EPI_STORE
+
+_BF16 = torch.bfloat16
+
+
+def compute_copy(p: torch.Tensor) -> torch.Tensor:
+    """bf16 view of a parameter for the GEMMs (cached on the tensor, keyed by its version)."""
+    if p.dtype == _BF16:
+        return p.detach()
+    cache = getattr(p, "_clipa_bf16", None)
+    if cache is None or cache[0] != p._version:
+        cache = (p._version, p.detach().to(_BF16))
+        p._clipa_bf16 = cache
+    return cache[1]
+
+
+def _f32(p: torch.Tensor) -> torch.Tensor:
+    """LayerNorm parameters are consumed in fp32 (reference keeps them fp32 in every mode)."""
+    return p.detach() if p.dtype == torch.float32 else p.detach().float()
+
+
+def _bias(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if p is None:
+        return None
+    return p.detach() if p.dtype in (_BF16, torch.float32) else p.detach().float()
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """dW[out,in] = dy[M,out]^T @ x[M,in]: both operands consumed MN-major, split-K, fp32 atomics."""
+    dw = torch.zeros(dy.shape[1], x.shape[1], dtype=torch.float32, device=dy.device)
+    ops.gemm(dy.t(), x.t(), dw, epilogue=EPI_ATOMIC_F32, split_k=-1)
+    return dw if like.dtype == torch.float32 else dw.to(like.dtype)
+
+
+def _bgrad(dy: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    db = torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
+    ops.colsum_accum(dy, db)
+    return db if like.dtype == torch.float32 else db.to(like.dtype)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x @ W^T (+ b).  `weight` is [out, in] (nn.Linear) or, with transposed=True, [in, out]
+    (the `x @ proj` convention of visual.proj / text_projection, open_clip/transformer.py:529)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, transposed):
+        w = compute_copy(weight)
+        wb = w.t() if transposed else w            # logical [out, in]
+        y = torch.empty(x.shape[0], wb.shape[0], dtype=_BF16, device=x.device)
+        ops.gemm(x, wb, y, bias=_bias(bias))
+        ctx.save_for_backward(x, weight, bias)
+        ctx.transposed = transposed
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias = ctx.saved_tensors
+        dy = dy.contiguous()
+        w = compute_copy(weight)
+        wb = w.t() if ctx.transposed else w        # [out, in]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            ops.gemm(dy, wb.t(), dx)               # dx[M,in] = dy[M,out] @ W[out,in]
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dy, x, weight)             # [out, in]
+            if ctx.transposed:
+                dw = dw.t().contiguous()
+        if bias is not None and ctx.needs_input_grad[2]:
+            db = _bgrad(dy, bias)
+        return dx, dw, db, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        y, mean, rstd = ops.layernorm_fwd(x, _f32(weight), _f32(bias), eps)
+        ctx.save_for_backward(x, weight, bias, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, mean, rstd = ctx.saved_tensors
+        D = x.shape[-1]
+        dg = torch.zeros(D, dtype=torch.float32, device=x.device)
+        db = torch.zeros(D, dtype=torch.float32, device=x.device)
+        dx = ops.layernorm_bwd(dy.contiguous(), x, _f32(weight), mean, rstd, None, dg, db)
+        return dx, dg.to(weight.dtype), db.to(bias.dtype), None
+
+
+class ResidualBlockFn(torch.autograd.Function):
+    """ResidualAttentionBlock.forward (open_clip/transformer.py:238-250) as one autograd node.
+
+    Saved for backward: block input x, packed qkv, attention output, x1 (post-attention residual),
+    the attention log-sum-exp and the LayerNorm statistics -- 6 activation-sized tensors.  The two
+    LayerNorm outputs and the c_fc GEMM + activation are recomputed in backward (+11% FLOPs)
+    instead of keeping the 4x-wide MLP activations resident.
+    """
+
+    @staticmethod
+    def forward(ctx, x, ln1_w, ln1_b, w_in, b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj,
+                b_proj, batch, seq, heads, causal, act):
+        M, D = x.shape
+        dev = x.device
+        h1, mean1, rstd1 = ops.layernorm_fwd(x, _f32(ln1_w), _f32(ln1_b))
+        qkv = torch.empty(M, 3 * D, dtype=_BF16, device=dev)
+        ops.gemm(h1, compute_copy(w_in), qkv, bias=_bias(b_in))
+        del h1
+        o, lse = ops.attention_fwd(qkv, batch, seq, heads, causal)
+        x1 = torch.empty(M, D, dtype=_BF16, device=dev)
+        ops.gemm(o, compute_copy(w_out), x1, bias=_bias(b_out), residual=x)
+        h2, mean2, rstd2 = ops.layernorm_fwd(x1, _f32(ln2_w), _f32(ln2_b))
+        g = torch.empty(M, w_fc.shape[0], dtype=_BF16, device=dev)
+        ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), act=act)
+        del h2
+        y = torch.empty(M, D, dtype=_BF16, device=dev)
+        ops.gemm(g, compute_copy(w_proj), y, bias=_bias(b_proj), residual=x1)
+        del g
+        ctx.save_for_backward(x, qkv, o, lse, x1, mean1, rstd1, mean2, rstd2, ln1_w, ln1_b, w_in,
+                              b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj)
+        ctx.meta = (batch, seq, heads, causal, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x, qkv, o, lse, x1, mean1, rstd1, mean2, rstd2, ln1_w, ln1_b, w_in, b_in, w_out, b_out,
+         ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj) = ctx.saved_tensors
+        batch, seq, heads, causal, act = ctx.meta
+        M, D = x.shape
+        dev = x.device
+        dy = dy.contiguous()
+        H4 = w_fc.shape[0]
+        # ---- MLP: recompute h2, f = c_fc(h2), g = act(f)
+        h2, _, _ = ops.layernorm_fwd(x1, _f32(ln2_w), _f32(ln2_b), save_stats=False)
+        f = torch.empty(M, H4, dtype=_BF16, device=dev)
+        g = torch.empty(M, H4, dtype=_BF16, device=dev)
+        ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), aux=f, act=act)
+        d_w_proj = _wgrad(dy, g, w_proj)
+        d_b_proj = _bgrad(dy, b_proj)
+        del g
+        df = torch.empty(M, H4, dtype=_BF16, device=dev)
+        ops.gemm(dy, compute_copy(w_proj).t(), df, epilogue=EPI_DACT, aux=f, act=act)
+        del f
+        d_w_fc = _wgrad(df, h2, w_fc)
+        d_b_fc = _bgrad(df, b_fc)
+        del h2
+        dh2 = torch.empty(M, D, dtype=_BF16, device=dev)
+        ops.gemm(df, compute_copy(w_fc).t(), dh2)
+        del df
+        d_ln2_w = torch.zeros(D, dtype=torch.float32, device=dev)
+        d_ln2_b = torch.zeros(D, dtype=torch.float32, device=dev)
+        dx1 = ops.layernorm_bwd(dh2, x1, _f32(ln2_w), mean2, rstd2, dy, d_ln2_w, d_ln2_b)
+        del dh2
+        # ---- attention
+        d_w_out = _wgrad(dx1, o, w_out)
+        d_b_out = _bgrad(dx1, b_out)
+        do = torch.empty(M, D, dtype=_BF16, device=dev)
+        ops.gemm(dx1, compute_copy(w_out).t(), do)
+        dqkv = ops.attention_bwd(qkv, o, do, lse, batch, seq, heads, causal)
+        del do
+        h1, _, _ = ops.layernorm_fwd(x, _f32(ln1_w), _f32(ln1_b), save_stats=False)
+        d_w_in = _wgrad(dqkv, h1, w_in)
+        d_b_in = _bgrad(dqkv, b_in)
+        del h1
+        dh1 = torch.empty(M, D, dtype=_BF16, device=dev)
+        ops.gemm(dqkv, compute_copy(w_in).t(), dh1)
+        del dqkv
+        d_ln1_w = torch.zeros(D, dtype=torch.float32, device=dev)
+        d_ln1_b = torch.zeros(D, dtype=torch.float32, device=dev)
+        dx = ops.layernorm_bwd(dh1, x, _f32(ln1_w), mean1, rstd1, dx1, d_ln1_w, d_ln1_b)
+        return (dx, d_ln1_w.to(ln1_w.dtype), d_ln1_b.to(ln1_b.dtype), d_w_in, d_b_in, d_w_out, d_b_out,
+                d_ln2_w.to(ln2_w.dtype), d_ln2_b.to(ln2_b.dtype), d_w_fc, d_b_fc, d_w_proj, d_b_proj,
+                None, None, None, None, None)
+
+
+class ClipLossFn(torch.autograd.Function):
+    """ClipLoss.forward (open_clip/loss.py:128-157), local-loss form: loss and all gradients are
+    produced in ONE pass over the (never materialised in forward) [B_local x B_global] logits.
+
+    image_features / text_features: LOCAL rows, bf16 [B_local, E], L2-normalised.
+    all_image / all_text: gathered [B_global, E] (the same tensors when world_size == 1).
+    Returns the fp32 scalar loss; saves d(local feats), d(gathered feats), d(logit_scale).
+    """
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, all_image, all_text, logit_scale, rank,
+                need_all_grads):
+        bl, E = image_features.shape
+        bg = all_image.shape[0]
+        s = float(logit_scale)
+        off = rank * bl if bg != bl else 0
+        dev = image_features.device
+        img, txt = image_features.contiguous(), text_features.contiguous()
+        aimg, atxt = all_image.contiguous(), all_text.contiguous()
+        lse_i, diag_i = ops.clip_lse(img, atxt, s, off)
+        lse_t, diag_t = ops.clip_lse(txt, aimg, s, off)
+        loss = 0.5 * ((lse_i - diag_i).mean() + (lse_t - diag_t).mean())
+        # gradients (scaled by grad_output in backward)
+        ds = torch.zeros(1, dtype=torch.float32, device=dev)
+        c = 0.5 / bl
+        p_i = ops.clip_softmax_grad(img, atxt, s, off, lse_i, ds)   # [bl, bg] bf16
+        p_t = ops.clip_softmax_grad(txt, aimg, s, off, lse_t, ds)
+        d_img = torch.empty(bl, E, dtype=torch.float32, device=dev)
+        d_txt = torch.empty(bl, E, dtype=torch.float32, device=dev)
+        ops.gemm(p_i, atxt.t(), d_img, alpha=c * s)                 # dI = c*s * Pi @ T_all
+        ops.gemm(p_t, aimg.t(), d_txt, alpha=c * s)                 # dT = c*s * Pt @ I_all
+        d_all_img = d_all_txt = None
+        if need_all_grads:
+            d_all_txt = torch.empty(bg, E, dtype=torch.float32, device=dev)
+            d_all_img = torch.empty(bg, E, dtype=torch.float32, device=dev)
+            ops.gemm(p_i.t(), img.t(), d_all_txt, alpha=c * s)      # dT_all = c*s * Pi^T @ I
+            ops.gemm(p_t.t(), txt.t(), d_all_img, alpha=c * s)      # dI_all = c*s * Pt^T @ T
+        ctx.save_for_backward(d_img, d_txt, d_all_img, d_all_txt, ds * c)
+        ctx.dtypes = (image_features.dtype, logit_scale.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        d_img, d_txt, d_all_img, d_all_txt, ds = ctx.saved_tensors
+        fdt, sdt = ctx.dtypes
+        g = gout.float()
+        return ((d_img * g).to(fdt), (d_txt * g).to(fdt),
+                None if d_all_img is None else (d_all_img * g).to(fdt),
+                None if d_all_txt is None else (d_all_txt * g).to(fdt),
+                (ds * g).reshape(()).to(sdt), None, None)

@@ -1,0 +1,8 @@
+"""Mirror of the `open_clip` surface that clipa_torch/training consumes (open_clip/__init__.py:1-13)."""
+from .factory import (add_model_config, create_loss, create_model, create_model_and_transforms,
+                      get_model_config, get_tokenizer, list_models, load_checkpoint)
+from .loss import ClipLoss, gather_features
+from .model import (CLIP, CLIPTextCfg, CLIPVisionCfg, convert_weights_to_fp16, convert_weights_to_lp,
+                    get_cast_dtype)
+from .transformer import (LayerNorm, LayerNormFp32, ResidualAttentionBlock, TextTransformer, Transformer,
+                          VisionTransformer)

@@ -1,0 +1,216 @@
+"""CLIP model with the reference's public surface (open_clip/model.py:200-274): same constructor
+arguments, attributes, parameter names and return conventions; the towers run on the B200
+kernels (clipa_b200.functional)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import functional as Fn
+from .transformer import LayerNorm, TextTransformer, VisionTransformer
+
+
+@dataclass
+class CLIPVisionCfg:
+    """Fields of open_clip/model.py:25-50 that the ViT path uses (others are accepted and must stay
+    at their defaults: timm / attentional-pool / patchnorm towers are out of scope)."""
+    layers: Union[Tuple[int, int, int, int], int] = 12
+    width: int = 768
+    head_width: int = 64
+    mlp_ratio: float = 4.0
+    patch_size: int = 16
+    image_size: Union[Tuple[int, int], int] = 224
+    ls_init_value: Optional[float] = None
+    patch_dropout: float = 0.
+    input_patchnorm: bool = False
+    global_average_pool: bool = False
+    attentional_pool: bool = False
+    n_queries: int = 256
+    attn_pooler_heads: int = 8
+    timm_model_name: str = None
+    timm_model_pretrained: bool = False
+    timm_pool: str = 'avg'
+    timm_proj: str = 'linear'
+    timm_proj_bias: bool = False
+    timm_drop: float = 0.
+    timm_drop_path: Optional[float] = None
+    output_tokens: bool = False
+    pos_embed: str = 'learnable'
+    gelu_approximate: str = 'none'
+    ln_pre: bool = True
+    pool_style: str = 'open_clip'
+
+
+@dataclass
+class CLIPTextCfg:
+    """open_clip/model.py:53-75."""
+    context_length: int = 77
+    vocab_size: int = 49408
+    width: int = 512
+    heads: int = 8
+    layers: int = 12
+    ls_init_value: Optional[float] = None
+    hf_model_name: str = None
+    hf_tokenizer_name: str = None
+    hf_model_pretrained: bool = True
+    proj: str = 'mlp'
+    pooler_type: str = 'mean_pooler'
+    embed_cls: bool = False
+    pad_id: int = 0
+    output_tokens: bool = False
+    text_mask: str = 'first'
+    gelu_approximate: str = 'none'
+    pool_style: str = 'open_clip'
+    bert_tokenizer: bool = False
+    vocab_path: str = None
+    attention_mask: bool = True
+
+
+def get_cast_dtype(precision: str):
+    """open_clip/model.py:78-86."""
+    if precision == 'bf16':
+        return torch.bfloat16
+    if precision == 'fp16':
+        raise NotImplementedError("fp16 is not built: the sm_100a kernels are bf16 (tcgen05 kind::f16 with bf16 operands)")
+    return None
+
+
+def _act_name(quick_gelu: bool, gelu_approximate: str) -> str:
+    if quick_gelu:
+        return "quick_gelu"
+    return {"none": "gelu", "tanh": "gelu_tanh"}[gelu_approximate]
+
+
+def _build_vision_tower(embed_dim, vision_cfg, quick_gelu=False, cast_dtype=None):
+    if isinstance(vision_cfg, dict):
+        vision_cfg = CLIPVisionCfg(**vision_cfg)
+    if vision_cfg.timm_model_name or isinstance(vision_cfg.layers, (tuple, list)) or \
+            vision_cfg.attentional_pool or vision_cfg.input_patchnorm:
+        raise NotImplementedError("only the ViT tower of the CLIPA hot path is built (no timm / ResNet / "
+                                  "attentional pool / patchnorm)")
+    return VisionTransformer(
+        image_size=vision_cfg.image_size, patch_size=vision_cfg.patch_size, width=vision_cfg.width,
+        layers=vision_cfg.layers, heads=vision_cfg.width // vision_cfg.head_width,
+        mlp_ratio=vision_cfg.mlp_ratio, ls_init_value=vision_cfg.ls_init_value,
+        patch_dropout=vision_cfg.patch_dropout, global_average_pool=vision_cfg.global_average_pool,
+        output_tokens=vision_cfg.output_tokens, output_dim=embed_dim,
+        act=_act_name(quick_gelu, vision_cfg.gelu_approximate), pos_embed=vision_cfg.pos_embed,
+        ln_pre=vision_cfg.ln_pre, pool_style=vision_cfg.pool_style)
+
+
+def _build_text_tower(embed_dim, text_cfg, quick_gelu=False, cast_dtype=None):
+    if isinstance(text_cfg, dict):
+        text_cfg = CLIPTextCfg(**text_cfg)
+    if text_cfg.hf_model_name:
+        raise NotImplementedError("HF text towers are out of scope")
+    return TextTransformer(
+        context_length=text_cfg.context_length, vocab_size=text_cfg.vocab_size, width=text_cfg.width,
+        heads=text_cfg.heads, layers=text_cfg.layers, ls_init_value=text_cfg.ls_init_value,
+        output_dim=embed_dim, embed_cls=text_cfg.embed_cls, pad_id=text_cfg.pad_id,
+        act=_act_name(quick_gelu, text_cfg.gelu_approximate), pool_style=text_cfg.pool_style,
+        attention_mask=text_cfg.attention_mask)
+
+
+def _l2_normalize(x: torch.Tensor) -> torch.Tensor:
+    """F.normalize(dim=-1) (open_clip/model.py:240,263); the norm is taken in fp32, the result is
+    rounded once to the feature dtype (bf16) that the contrastive-head GEMM consumes."""
+    return F.normalize(x.float(), dim=-1).to(x.dtype)
+
+
+class CLIP(nn.Module):
+    """open_clip/model.py:200-274."""
+
+    def __init__(self, embed_dim: int, vision_cfg: CLIPVisionCfg, text_cfg: CLIPTextCfg,
+                 quick_gelu: bool = False, cast_dtype: Optional[torch.dtype] = None,
+                 output_dict: bool = False):
+        super().__init__()
+        self.output_dict = output_dict
+        self.visual = _build_vision_tower(embed_dim, vision_cfg, quick_gelu, cast_dtype)
+        text = _build_text_tower(embed_dim, text_cfg, quick_gelu, cast_dtype)
+        self.transformer = text.transformer
+        self.context_length = text.context_length
+        self.vocab_size = text.vocab_size
+        self.token_embedding = text.token_embedding
+        self.positional_embedding = text.positional_embedding
+        self.ln_final = text.ln_final
+        self.text_projection = text.text_projection
+        self.pool_style = text.pool_style
+        self.register_buffer('attn_mask', text.attn_mask, persistent=False)
+        self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
+
+    def lock_image_tower(self, unlocked_groups=0, freeze_bn_stats=False):
+        self.visual.lock(unlocked_groups=unlocked_groups, freeze_bn_stats=freeze_bn_stats)
+
+    @torch.jit.ignore
+    def set_grad_checkpointing(self, enable=True):
+        self.visual.set_grad_checkpointing(enable)
+        self.transformer.grad_checkpointing = enable
+
+    def encode_image(self, image, normalize: bool = False):
+        features = self.visual(image)
+        return _l2_normalize(features) if normalize else features
+
+    def encode_text(self, text, normalize: bool = False):
+        N, L = text.shape
+        if L != self.context_length:
+            raise ValueError(f"text length {L} != context_length {self.context_length} "
+                             "(the reference adds the full positional embedding, model.py:247)")
+        x = self.token_embedding(text).to(torch.bfloat16)
+        x = x + self.positional_embedding.to(torch.bfloat16)
+        W = x.shape[-1]
+        causal = self.attn_mask is not None
+        x = self.transformer(x.reshape(N * L, W).contiguous(), N, L, causal=causal).reshape(N, L, W)
+        # ln_final is row-wise, so normalising only the pooled rows equals model.py:251-254
+        if self.pool_style == 'open_clip':
+            pooled = x[torch.arange(N, device=x.device), text.argmax(dim=-1)]
+        elif self.pool_style == 'big_vision_tok':
+            pooled = x[:, 0]
+        elif self.pool_style == 'big_vision_last':
+            pooled = x[:, -1]
+        else:
+            raise ValueError(self.pool_style)
+        pooled = self.ln_final(pooled.contiguous())
+        x = Fn.LinearFn.apply(pooled, self.text_projection, None, True)
+        return _l2_normalize(x) if normalize else x
+
+    def forward(self, image, text):
+        image_features = self.encode_image(image, normalize=True)
+        text_features = self.encode_text(text, normalize=True)
+        if self.output_dict:
+            return {"image_features": image_features, "text_features": text_features,
+                    "logit_scale": self.logit_scale.exp()}
+        return image_features, text_features, self.logit_scale.exp()
+
+
+def convert_weights_to_lp(model: nn.Module, dtype=torch.bfloat16):
+    """open_clip/model.py:329-351: Linear / Conv / MultiheadAttention weights+biases and the two
+    projection matrices go to low precision; LayerNorm, embeddings, positional/class embeddings
+    and logit_scale stay fp32."""
+
+    def _convert(l):
+        if isinstance(l, (nn.Conv1d, nn.Conv2d, nn.Linear)):
+            l.weight.data = l.weight.data.to(dtype)
+            if l.bias is not None:
+                l.bias.data = l.bias.data.to(dtype)
+        if isinstance(l, nn.MultiheadAttention):
+            for attr in ["in_proj_weight", "in_proj_bias", "bias_k", "bias_v"]:
+                tensor = getattr(l, attr, None)
+                if tensor is not None:
+                    tensor.data = tensor.data.to(dtype)
+            l.out_proj.weight.data = l.out_proj.weight.data.to(dtype)
+            l.out_proj.bias.data = l.out_proj.bias.data.to(dtype)
+        for name in ["text_projection", "proj"]:
+            if hasattr(l, name):
+                attr = getattr(l, name)
+                if isinstance(attr, nn.Parameter):
+                    attr.data = attr.data.to(dtype)
+
+    model.apply(_convert)
+
+
+convert_weights_to_fp16 = convert_weights_to_lp

@@ -1,0 +1,244 @@
+"""Transformer towers with the reference's module/parameter names (open_clip/transformer.py) and
+the B200 kernels underneath.
+
+The nn.Module tree (and therefore the state_dict keys, the weight-decay split on parameter names,
+DDP wrapping, checkpoints) is the reference's: ln_1 / attn.in_proj_weight / attn.out_proj /
+ln_2 / mlp.c_fc / mlp.c_proj per block.  torch.nn modules are used as PARAMETER CONTAINERS with
+their stock initialisation; their forward() is never called -- each block is one
+clipa_b200.functional.ResidualBlockFn node.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import functional as Fn
+from ..ops import ACT_BY_NAME
+from .pos_embed import get_2d_sincos_pos_embed
+
+
+def to_2tuple(x):
+    return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+
+
+class LayerNorm(nn.LayerNorm):
+    """open_clip/transformer.py:19-34 (LayerNorm and LayerNormFp32 collapse into one kernel:
+    statistics are always fp32, output is cast back to the input dtype).  x: [..., D] bf16."""
+
+    def forward(self, x: torch.Tensor):
+        shape = x.shape
+        y = Fn.LayerNormFn.apply(x.reshape(-1, shape[-1]).contiguous(), self.weight, self.bias, self.eps)
+        return y.reshape(shape)
+
+
+LayerNormFp32 = LayerNorm
+
+
+class ResidualAttentionBlock(nn.Module):
+    """open_clip/transformer.py:195-250 (self-attention form; ls_1/ls_2 are Identity as in every
+    shipped CLIPA config)."""
+
+    def __init__(self, d_model: int, n_head: int, mlp_ratio: float = 4.0, ls_init_value: float = None,
+                 act: str = "gelu", is_cross_attention: bool = False):
+        super().__init__()
+        if ls_init_value is not None or is_cross_attention:
+            raise NotImplementedError("LayerScale / cross-attention blocks are outside the CLIPA hot path")
+        self.ln_1 = LayerNorm(d_model)
+        self.attn = nn.MultiheadAttention(d_model, n_head)   # parameter container only
+        self.ln_2 = LayerNorm(d_model)
+        mlp_width = int(d_model * mlp_ratio)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("c_fc", nn.Linear(d_model, mlp_width)),
+            ("gelu", nn.Identity()),                           # activation is fused into the c_fc GEMM
+            ("c_proj", nn.Linear(mlp_width, d_model)),
+        ]))
+        self.n_head = n_head
+        self.act = ACT_BY_NAME[act]
+
+    def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool):
+        """x: [batch*seq, d_model] bf16, sample-major rows."""
+        return Fn.ResidualBlockFn.apply(
+            x, self.ln_1.weight, self.ln_1.bias, self.attn.in_proj_weight, self.attn.in_proj_bias,
+            self.attn.out_proj.weight, self.attn.out_proj.bias, self.ln_2.weight, self.ln_2.bias,
+            self.mlp.c_fc.weight, self.mlp.c_fc.bias, self.mlp.c_proj.weight, self.mlp.c_proj.bias,
+            batch, seq, self.n_head, causal, self.act)
+
+
+class Transformer(nn.Module):
+    """open_clip/transformer.py:294-326.  `grad_checkpointing` is accepted for API parity; the block
+    function already recomputes its MLP activations, so the flag does not change the math."""
+
+    def __init__(self, width: int, layers: int, heads: int, mlp_ratio: float = 4.0,
+                 ls_init_value: float = None, act: str = "gelu"):
+        super().__init__()
+        self.width = width
+        self.layers = layers
+        self.grad_checkpointing = False
+        self.resblocks = nn.ModuleList([
+            ResidualAttentionBlock(width, heads, mlp_ratio, ls_init_value=ls_init_value, act=act)
+            for _ in range(layers)])
+
+    def get_cast_dtype(self) -> torch.dtype:
+        return self.resblocks[0].mlp.c_fc.weight.dtype
+
+    def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool = False):
+        for r in self.resblocks:
+            x = r(x, batch, seq, causal)
+        return x
+
+
+class VisionTransformer(nn.Module):
+    """open_clip/transformer.py:329-534 (no attentional pool, no input patchnorm)."""
+
+    def __init__(self, image_size: int, patch_size: int, width: int, layers: int, heads: int,
+                 mlp_ratio: float, ls_init_value: float = None, global_average_pool: bool = False,
+                 output_dim: int = 512, patch_dropout: float = 0., act: str = "gelu",
+                 pos_embed: str = "learnable", ln_pre: bool = True, pool_style: str = "open_clip",
+                 output_tokens: bool = False):
+        super().__init__()
+        if patch_dropout > 0.:
+            raise NotImplementedError("PatchDropout is a 'next' row of the scope table (SURVEY 8f.4)")
+        self.output_tokens = output_tokens
+        image_height, image_width = self.image_size = to_2tuple(image_size)
+        patch_height, patch_width = self.patch_size = to_2tuple(patch_size)
+        self.grid_size = (image_height // patch_height, image_width // patch_width)
+        self.output_dim = output_dim
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)  # container
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        n_pos = self.grid_size[0] * self.grid_size[1] + 1
+        if pos_embed == "learnable":
+            self.positional_embedding = nn.Parameter(scale * torch.randn(n_pos, width))
+        elif pos_embed == "sin_cos_2d":
+            assert self.grid_size[0] == self.grid_size[1], "sin-cos 2d position embedding needs a square grid"
+            self.positional_embedding = nn.Parameter(
+                get_2d_sincos_pos_embed(width, self.grid_size[0], cls_token=True), requires_grad=False)
+        else:
+            raise NotImplementedError(pos_embed)
+        self.ln_pre = LayerNorm(width) if ln_pre else nn.Identity()
+        self.transformer = Transformer(width, layers, heads, mlp_ratio, ls_init_value=ls_init_value, act=act)
+        self.global_average_pool = global_average_pool
+        self.attn_pool = None
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self.pool_style = pool_style
+        self.width = width
+
+    def lock(self, unlocked_groups=0, freeze_bn_stats=False):
+        """LiT-style freezing, open_clip/transformer.py:415-446."""
+        for p in self.parameters():
+            p.requires_grad = False
+        if unlocked_groups != 0:
+            groups = [[self.conv1, self.class_embedding, self.positional_embedding, self.ln_pre],
+                      *self.transformer.resblocks[:-1],
+                      [self.transformer.resblocks[-1], self.ln_post], self.proj]
+
+            def _unlock(x):
+                if isinstance(x, (list, tuple)):
+                    for g in x:
+                        _unlock(g)
+                elif isinstance(x, nn.Parameter):
+                    x.requires_grad = True
+                else:
+                    for p in x.parameters():
+                        p.requires_grad = True
+            _unlock(groups[-unlocked_groups:])
+
+    @torch.jit.ignore
+    def set_grad_checkpointing(self, enable=True):
+        self.transformer.grad_checkpointing = enable
+
+    def _global_pool(self, x: torch.Tensor, include_cls=True) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.global_average_pool and not include_cls:
+            return x[:, 1:].float().mean(dim=1).to(x.dtype), x[:, 1:]
+        if self.global_average_pool and include_cls:
+            return x.float().mean(dim=1).to(x.dtype), x
+        return x[:, 0], x[:, 1:]
+
+    def forward(self, x: torch.Tensor):
+        N = x.shape[0]
+        ph, pw = self.patch_size
+        gh, gw = self.grid_size
+        W = self.width
+        # conv1 (stride == kernel, no bias) == patchify + GEMM (open_clip/transformer.py:371,491-493).
+        # K = 3*ph*pw is zero-padded to a multiple of 8 so TMA row pitches stay 16-byte aligned.
+        x = x.to(torch.bfloat16)
+        K = 3 * ph * pw
+        Kp = (K + 7) // 8 * 8
+        patches = x.reshape(N, 3, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(N * gh * gw, K)
+        wmat = self.conv1.weight.reshape(W, K)
+        if Kp != K:
+            patches = torch.nn.functional.pad(patches, (0, Kp - K))
+            wmat = torch.nn.functional.pad(wmat, (0, Kp - K))
+        tok = Fn.LinearFn.apply(patches.contiguous(), wmat, None, False).reshape(N, gh * gw, W)
+        cls = self.class_embedding.to(tok.dtype).reshape(1, 1, W).expand(N, 1, W)
+        x = torch.cat([cls, tok], dim=1) + self.positional_embedding.to(tok.dtype)
+        L = x.shape[1]
+        x = self.ln_pre(x)
+        x = self.transformer(x.reshape(N * L, W).contiguous(), N, L, causal=False).reshape(N, L, W)
+        if self.pool_style == "open_clip":
+            pooled, tokens = self._global_pool(x)
+            pooled = self.ln_post(pooled)
+        elif self.pool_style == "big_vision_tok":
+            assert not self.global_average_pool
+            x = self.ln_post(x)
+            pooled, tokens = self._global_pool(x)
+        elif self.pool_style == "big_vision_gap":
+            assert self.global_average_pool
+            pooled, tokens = self._global_pool(x, include_cls=False)
+            pooled = self.ln_post(pooled)
+        else:
+            raise ValueError(self.pool_style)
+        if self.proj is not None:
+            pooled = Fn.LinearFn.apply(pooled.contiguous(), self.proj, None, True)
+        if self.output_tokens:
+            return pooled, tokens
+        return pooled
+
+
+class TextTransformer(nn.Module):
+    """Parameter layout and init of open_clip/transformer.py:537-616; CLIP.__init__ re-homes these
+    members onto the CLIP module exactly like the reference (open_clip/model.py:216-225)."""
+
+    def __init__(self, context_length: int = 77, vocab_size: int = 49408, width: int = 512,
+                 heads: int = 8, layers: int = 12, ls_init_value: float = None, output_dim: int = 512,
+                 act: str = "gelu", embed_cls: bool = False, pad_id: int = 0,
+                 pool_style: str = "open_clip", attention_mask: bool = True):
+        super().__init__()
+        if embed_cls:
+            raise NotImplementedError("embed_cls (CoCa text tower) is outside the CLIPA hot path")
+        self.num_pos = self.context_length = context_length
+        self.vocab_size = vocab_size
+        self.width = width
+        self.output_dim = output_dim
+        self.heads = heads
+        self.pad_id = pad_id
+        self.pool_style = pool_style
+        self.text_projection = nn.Parameter(torch.empty(width, output_dim))
+        self.token_embedding = nn.Embedding(vocab_size, width)
+        self.positional_embedding = nn.Parameter(torch.empty(self.num_pos, width))
+        self.transformer = Transformer(width=width, layers=layers, heads=heads,
+                                       ls_init_value=ls_init_value, act=act)
+        self.ln_final = LayerNorm(width)
+        if attention_mask:
+            mask = torch.full((self.num_pos, self.num_pos), float("-inf")).triu_(1)
+            self.register_buffer("attn_mask", mask, persistent=False)
+        else:
+            self.attn_mask = None
+        self.init_parameters()
+
+    def init_parameters(self):
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        proj_std = (self.transformer.width ** -0.5) * ((2 * self.transformer.layers) ** -0.5)
+        attn_std = self.transformer.width ** -0.5
+        fc_std = (2 * self.transformer.width) ** -0.5
+        for block in self.transformer.resblocks:
+            nn.init.normal_(block.attn.in_proj_weight, std=attn_std)
+            nn.init.normal_(block.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(block.mlp.c_fc.weight, std=fc_std)
+            nn.init.normal_(block.mlp.c_proj.weight, std=proj_std)
+        nn.init.normal_(self.text_projection, std=self.transformer.width ** -0.5)

@@ -18,6 +18,23 @@ ACT_BY_NAME = {"gelu": ACT_GELU_ERF, "gelu_erf": ACT_GELU_ERF, "none": ACT_GELU_
                "gelu_tanh": ACT_GELU_TANH, "tanh": ACT_GELU_TANH, "quick_gelu": ACT_QUICK_GELU}
 
 
+class GemmProfiler:
+    """CUDA-event timing of every clipa_gemm launch on the launching stream (bench.py roofline)."""
+
+    def __init__(self):
+        self.records = []  # (flops, start_event, end_event)
+
+    def summary(self):
+        """-> (achieved TFLOP/s over all timed launches, total ms, number of launches)."""
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for _, s, e in self.records)
+        fl = sum(f for f, _, _ in self.records)
+        return (fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0), ms, len(self.records)
+
+
+PROFILER: Optional[GemmProfiler] = None
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -76,6 +93,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, epilogue: int =
     d.act = act
     d.split_k = split_k
     d.max_ctas = max_ctas
+    if PROFILER is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.lib().clipa_gemm(C.byref(d), _stream()), "clipa_gemm")
+        e1.record()
+        PROFILER.records.append((2.0 * M * N * K, e0, e1))
+        return out
     check(_lib.lib().clipa_gemm(C.byref(d), _stream()), "clipa_gemm")
     return out
 

@@ -1,0 +1,214 @@
+"""GPU parity tests of every C-ABI entry point against plain fp32 torch math of the same op
+(floating-point kernels: the fp32 reference is the oracle at this granularity; tolerances are
+bf16 round-off of the OUTPUT, stated per test)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_OUT = 1e-2     # max-abs error / max-abs value for a bf16-rounded output of O(1)-conditioned math
+F32_OUT = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def ops():
+    from clipa_b200 import ops as o
+    return o
+
+
+def relmax(got, ref):
+    got, ref = got.float(), ref.float()
+    assert torch.isfinite(got).all()
+    return ((got - ref).abs().max() / (ref.abs().max() + 1e-30)).item()
+
+
+def mk(shape, dev, scale=1.0, seed=None):
+    return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 1024), (128, 128, 128), (100, 256, 64),
+                                   (333, 776, 200), (1000, 88, 72), (129, 264, 1032), (82 * 7, 768, 768),
+                                   (4096, 3072, 1024)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+def test_gemm_majors(dev, M, N, K, a_mn, b_mn):
+    torch.manual_seed(M * 7 + N * 3 + K)
+    A = mk((K, M), dev).t() if a_mn else mk((M, K), dev)
+    B = mk((K, N), dev).t() if b_mn else mk((N, K), dev)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    ops().gemm(A, B, out)
+    assert relmax(out, A.float() @ B.float().t()) < BF16_OUT
+
+
+def test_gemm_epilogues(dev):
+    from clipa_b200._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_QUICK_GELU, EPI_ATOMIC_F32,
+                                 EPI_BIAS_ACT, EPI_DACT)
+    o = ops()
+    torch.manual_seed(1)
+    M, N, K = 1024, 1024, 512
+    A, B = mk((M, K), dev), mk((N, K), dev, 0.05)
+    bias = torch.randn(N, device=dev)
+    res = mk((M, N), dev)
+    ref = A.float() @ B.float().t()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    o.gemm(A, B, out, bias=bias, residual=res)
+    assert relmax(out, ref + bias + res.float()) < BF16_OUT
+    o.gemm(A, B, out, bias=bias.bfloat16(), alpha=0.5)
+    assert relmax(out, 0.5 * ref + bias.bfloat16().float()) < BF16_OUT
+    out32 = torch.empty(M, N, dtype=torch.float32, device=dev)
+    o.gemm(A, B, out32)
+    assert relmax(out32, ref) < F32_OUT
+    F = torch.nn.functional
+    for act, fn in [(ACT_GELU_ERF, lambda x: F.gelu(x)), (ACT_GELU_TANH, lambda x: F.gelu(x, approximate="tanh")),
+                    (ACT_QUICK_GELU, lambda x: x * torch.sigmoid(1.702 * x))]:
+        aux = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        o.gemm(A, B, out, epilogue=EPI_BIAS_ACT, bias=bias, aux=aux, act=act)
+        f = ref + bias
+        assert relmax(aux, f) < BF16_OUT
+        assert relmax(out, fn(f.bfloat16().float())) < BF16_OUT
+        out_noaux = torch.empty_like(out)
+        o.gemm(A, B, out_noaux, epilogue=EPI_BIAS_ACT, bias=bias, act=act)
+        assert relmax(out_noaux, fn(f)) < BF16_OUT
+        x = aux.float().requires_grad_(True)
+        fn(x).sum().backward()
+        W = mk((K, N), dev, 0.05)
+        out2 = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        o.gemm(A, W.t(), out2, epilogue=EPI_DACT, aux=aux, act=act)
+        assert relmax(out2, (A.float() @ W.float()) * x.grad) < BF16_OUT
+    Mt = 20000
+    dY, X = mk((Mt, 768), dev, 0.1), mk((Mt, 512), dev, 0.1)
+    acc = torch.zeros(768, 512, dtype=torch.float32, device=dev)
+    o.gemm(dY.t(), X.t(), acc, epilogue=EPI_ATOMIC_F32, split_k=-1)
+    o.gemm(dY.t(), X.t(), acc, epilogue=EPI_ATOMIC_F32, split_k=3, alpha=2.0)
+    assert relmax(acc, 3.0 * (dY.float().t() @ X.float())) < 1e-4
+
+
+def test_gemm_rejects_bad_arguments(dev):
+    from clipa_b200._lib import ClipaError
+    o = ops()
+    A, B = mk((64, 36), dev), mk((64, 36), dev)      # ld = 36 is not a multiple of 8
+    with pytest.raises(ClipaError):
+        o.gemm(A, B, torch.empty(64, 64, dtype=torch.bfloat16, device=dev))
+    with pytest.raises(ClipaError):                  # CPU tensors are refused, not silently handled
+        o.gemm(torch.zeros(64, 64, dtype=torch.bfloat16), torch.zeros(64, 64, dtype=torch.bfloat16),
+               torch.zeros(64, 64, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("rows,D", [(1000, 768), (4099, 1024), (513, 1280), (64, 512), (300, 256), (7, 1664)])
+def test_layernorm(dev, rows, D):
+    o = ops()
+    torch.manual_seed(rows + D)
+    x = mk((rows, D), dev, 2.0) + 0.5
+    g, b = torch.randn(D, device=dev), torch.randn(D, device=dev)
+    y, mean, rstd = o.layernorm_fwd(x, g, b)
+    xr, gr, br = x.float().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-5)
+    assert relmax(y, yr) < BF16_OUT
+    assert relmax(mean, xr.mean(-1)) < F32_OUT
+    dy, dres = mk((rows, D), dev), mk((rows, D), dev)
+    yr.backward(dy.float())
+    dg, db = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    dx = o.layernorm_bwd(dy, x, g, mean, rstd, dres, dg, db)
+    assert relmax(dx, xr.grad + dres.float()) < BF16_OUT
+    assert relmax(dg, gr.grad) < 1e-3 and relmax(db, br.grad) < 1e-3
+
+
+def test_layernorm_constant_rows(dev):
+    """Size-independent property: a constant row normalises to exactly beta."""
+    o = ops()
+    D = 1024
+    x = torch.full((33, D), 3.25, device=dev).bfloat16()
+    g, b = torch.randn(D, device=dev), torch.randn(D, device=dev)
+    y, _, _ = o.layernorm_fwd(x, g, b)
+    assert torch.equal(y, b.bfloat16().expand(33, D))
+
+
+def test_colsum(dev):
+    o = ops()
+    x = mk((5000, 776), dev)
+    out = torch.ones(776, device=dev)
+    o.colsum_accum(x, out)
+    assert relmax(out, 1.0 + x.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("B,L,H,hd,causal", [(3, 82, 16, 64, False), (5, 16, 12, 64, True), (2, 37, 16, 80, False),
+                                             (2, 257, 4, 64, False), (4, 8, 16, 64, True), (2, 65, 12, 64, False),
+                                             (3, 32, 12, 64, True), (2, 100, 2, 64, True), (1, 1, 2, 64, True)])
+def test_attention(dev, B, L, H, hd, causal):
+    o = ops()
+    torch.manual_seed(B * 100 + L)
+    D = H * hd
+    qkv = mk((B * L, 3 * D), dev)
+    out, lse = o.attention_fwd(qkv, B, L, H, causal)
+    x = qkv.float().reshape(B, L, 3, H, hd).requires_grad_(True)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device=dev).triu(1)
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * L, D)
+    assert relmax(out, ref) < 2e-2
+    assert relmax(lse, torch.logsumexp(s, -1)) < 1e-4
+    dout = mk((B * L, D), dev)
+    ref.backward(dout.float())
+    dqkv = o.attention_bwd(qkv, out, dout, lse, B, L, H, causal)
+    gref = x.grad.reshape(B * L, 3 * D)
+    for i in range(3):
+        assert relmax(dqkv[:, i * D:(i + 1) * D], gref[:, i * D:(i + 1) * D]) < 3e-2
+
+
+def test_attention_uniform_values(dev):
+    """Property at full per-GPU size of config 3 (B=4096 x 16 heads would be 10 GB of qkv; one
+    eighth here): if every key carries the same value row, attention returns exactly that row."""
+    o = ops()
+    B, L, H, hd = 512, 82, 16, 64
+    D = H * hd
+    qkv = mk((B * L, 3 * D), dev)
+    vrow = torch.randn(D, device=dev).bfloat16()
+    qkv[:, 2 * D:] = vrow
+    out, _ = o.attention_fwd(qkv, B, L, H, False)
+    assert relmax(out, vrow.float().expand(B * L, D)) < 1e-2
+
+
+@pytest.mark.parametrize("bl,bg,E,off", [(256, 256, 512, 0), (300, 1000, 768, 300), (1024, 4096, 768, 2048),
+                                         (8, 8, 64, 0), (130, 260, 1024, 130)])
+def test_clip_head_kernels(dev, bl, bg, E, off):
+    o = ops()
+    torch.manual_seed(bl + bg)
+    a = torch.nn.functional.normalize(torch.randn(bl, E, device=dev), dim=-1).bfloat16()
+    b = torch.nn.functional.normalize(torch.randn(bg, E, device=dev), dim=-1).bfloat16()
+    scale = 14.285714
+    logits = scale * (a.float() @ b.float().t())
+    idx = torch.arange(bl, device=dev)
+    lse, diag = o.clip_lse(a, b, scale, off)
+    assert relmax(lse, torch.logsumexp(logits, -1)) < F32_OUT
+    assert relmax(diag, logits[idx, idx + off]) < F32_OUT
+    ds = torch.zeros(1, device=dev)
+    pt = o.clip_softmax_grad(a, b, scale, off, lse, ds)
+    p_ref = torch.softmax(logits, -1)
+    p_ref[idx, idx + off] -= 1.0
+    assert relmax(pt, p_ref) < BF16_OUT
+    assert relmax(ds, (p_ref * logits / scale).sum().reshape(1)) < 2e-3
+
+
+def test_clip_loss_identical_pairs_full_size(dev):
+    """BASELINE size (B_local 4096 x B_global 32768, E 768): with identical samples every logit is
+    equal, so both cross-entropies are ln(B_global) -- the reference's SyntheticDataset property
+    (training/data.py:469-486)."""
+    from clipa_b200.open_clip import ClipLoss
+    bl, bg, E = 4096, 32768, 768
+    v = torch.nn.functional.normalize(torch.randn(1, E, device=dev), dim=-1).bfloat16()
+    a, b = v.expand(bl, E).contiguous(), v.expand(bg, E).contiguous()
+    lse, diag = ops().clip_lse(a, b, 14.285714, 4096)
+    loss = (lse - diag).mean().item()
+    assert abs(loss - math.log(bg)) < 1e-4
+    # and through the public module at world_size 1 (8192 pairs)
+    f = v.expand(8192, E).contiguous().requires_grad_(True)
+    out = ClipLoss()(f, f, torch.tensor(14.285714, device=dev))
+    assert abs(out.item() - math.log(8192)) < 1e-4
