@@ -139,7 +139,31 @@ def make_ddp_loss_golden():
     print("wrote cliploss_world2_gloo.npz", {k: float(res[k]) for k in ("loss_r0", "loss_r1")})
 
 
+def make_schema_golden(open_clip):
+    """state_dict keys / shapes and the dtype policy of precision='bf16' as the reference builds them
+    (the drop-in contract for checkpoints and for the weight-decay split on parameter names)."""
+    out = {}
+    for name, cfg, image_size in (("tiny-cls", TINY_CONFIGS["tiny-cls"], 64), ("ViT-B-32-ctx16", CONFIG1, 192)):
+        tmp = Path(tempfile.mkdtemp())
+        (tmp / f"schema-{name}.json").write_text(json.dumps(cfg))
+        open_clip.add_model_config(tmp)
+        for precision in ("fp32", "bf16"):
+            m = open_clip.create_model(f"schema-{name}", precision=precision, device="cpu",
+                                       force_image_size=image_size, pos_embed="sin_cos_2d")
+            out[f"{name}/{precision}"] = {
+                "state_dict": {k: [list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()},
+                "requires_grad": {k: bool(p.requires_grad) for k, p in m.named_parameters()},
+                "buffers_non_persistent": [k for k, _ in m.named_buffers() if k not in m.state_dict()],
+            }
+    (GOLD / "reference_schema.json").write_text(json.dumps(out, indent=0))
+    print("wrote reference_schema.json")
+
+
 def main():
+    if "--schema-only" in sys.argv:
+        GOLD.mkdir(parents=True, exist_ok=True)
+        make_schema_golden(import_reference())
+        return
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -159,6 +183,7 @@ def main():
             np.savez_compressed(GOLD / f"{name}_{precision}.npz", meta=json.dumps(meta), **res)
             print(f"wrote {name}_{precision}.npz loss={float(res['loss']):.6f} ({loss_dtype})")
     make_ddp_loss_golden()
+    make_schema_golden(open_clip)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,97 @@
+"""CPU: host-side mirror of the reference interface -- registry, module tree / state_dict schema,
+precision policy, weight-decay grouping, position embedding -- against facts dumped from the
+reference (tests/golden/reference_schema.json, sincos_ref.npz)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from clipa_b200 import open_clip
+from oracle.weights import CONFIG1, TINY_CONFIGS
+from tests.helpers import GOLD
+
+
+@pytest.fixture(scope="module")
+def schema():
+    return json.loads((GOLD / "reference_schema.json").read_text())
+
+
+def _register(tmp_path, name, cfg):
+    p = tmp_path / f"{name}.json"
+    p.write_text(json.dumps(cfg))
+    open_clip.add_model_config(p)
+
+
+@pytest.mark.parametrize("name,cfg,size", [("tiny-cls", TINY_CONFIGS["tiny-cls"], 64), ("ViT-B-32-ctx16", CONFIG1, 192)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_state_dict_schema_and_dtypes_match_reference(tmp_path, schema, name, cfg, size, precision):
+    _register(tmp_path, f"schema-{name}", cfg)
+    m = open_clip.create_model(f"schema-{name}", precision=precision, device="cpu", force_image_size=size,
+                               pos_embed="sin_cos_2d")
+    ref = schema[f"{name}/{precision}"]
+    ours = {k: [list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()}
+    assert list(ours.keys()) == list(ref["state_dict"].keys())          # same keys, same order
+    assert ours == ref["state_dict"]                                    # same shapes and dtypes
+    assert {k: bool(p.requires_grad) for k, p in m.named_parameters()} == ref["requires_grad"]
+    assert [k for k, _ in m.named_buffers() if k not in m.state_dict()] == ref["buffers_non_persistent"]
+
+
+def test_builtin_registry_covers_baseline_configs():
+    want = {
+        "ViT-B-16-CL16": (768, 12, 512, 12, 16, 512),
+        "ViT-L-14-CL16": (1024, 24, 768, 12, 16, 768),
+        "ViT-L-14-CL32": (1024, 24, 768, 12, 32, 768),
+        "ViT-H-14-CL8-SyntaxMask-GAP": (1280, 32, 1024, 24, 8, 1024),
+        "ViT-L-14": (1024, 24, 768, 12, 77, 768),
+    }
+    for name, (vw, vl, tw, tl, ctx, e) in want.items():
+        c = open_clip.get_model_config(name)
+        assert c is not None, name
+        assert (c["vision_cfg"]["width"], c["vision_cfg"]["layers"], c["text_cfg"]["width"],
+                c["text_cfg"]["layers"], c["text_cfg"]["context_length"], c["embed_dim"]) == (vw, vl, tw, tl, ctx, e)
+    assert open_clip.get_model_config("ViT-H-14")["vision_cfg"]["head_width"] == 80
+    bv = open_clip.get_model_config("ViT-L-14-CL32-GAP-BigVision")
+    assert bv["vision_cfg"]["pool_style"] == "big_vision_gap" and bv["text_cfg"]["attention_mask"] is False
+    assert open_clip.get_model_config("no-such-model") is None
+    with pytest.raises(RuntimeError):
+        open_clip.create_model("no-such-model")
+
+
+def test_sincos_matches_reference():
+    from clipa_b200.open_clip.pos_embed import get_2d_sincos_pos_embed
+    z = np.load(GOLD / "sincos_ref.npz")
+    assert np.abs(get_2d_sincos_pos_embed(128, 3, True).numpy() - z["w128_g3"]).max() < 1e-6
+    assert np.abs(get_2d_sincos_pos_embed(768, 6, True).numpy() - z["w768_g6"]).max() < 1e-6
+
+
+def test_weight_decay_split_follows_reference_rule(tmp_path):
+    from clipa_b200.training import exclude_from_wd
+    _register(tmp_path, "wd-tiny", TINY_CONFIGS["tiny-cls"])
+    m = open_clip.create_model("wd-tiny")
+    no_decay = {n for n, p in m.named_parameters() if exclude_from_wd(n, p)}
+    assert "logit_scale" in no_decay and "visual.class_embedding" in no_decay
+    assert "visual.transformer.resblocks.0.ln_1.weight" in no_decay
+    assert "transformer.resblocks.1.mlp.c_fc.bias" in no_decay
+    assert "visual.transformer.resblocks.0.attn.in_proj_weight" not in no_decay
+    assert "visual.proj" not in no_decay and "token_embedding.weight" not in no_decay
+
+
+def test_unsupported_features_raise(tmp_path):
+    cfg = json.loads(json.dumps(TINY_CONFIGS["tiny-cls"]))
+    cfg["vision_cfg"]["timm_model_name"] = "resnet50"
+    _register(tmp_path, "bad-timm", cfg)
+    with pytest.raises(NotImplementedError):
+        open_clip.create_model("bad-timm")
+    with pytest.raises(NotImplementedError):
+        open_clip.create_model("ViT-B-32", precision="fp16")
+    with pytest.raises(NotImplementedError):
+        open_clip.create_model("ViT-B-32", force_patch_dropout=0.5)
+
+
+def test_create_loss_signature():
+    from types import SimpleNamespace
+    args = SimpleNamespace(distill=False, model="ViT-L-14", local_loss=True, gather_with_grad=True, rank=3,
+                           world_size=8, horovod=False)
+    loss = open_clip.create_loss(args)
+    assert isinstance(loss, open_clip.ClipLoss) and loss.rank == 3 and loss.world_size == 8 and loss.local_loss
