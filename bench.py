@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--op-table", default=None, help="write the per-kernel CUDA-event table (JSON) to this path")
     args = ap.parse_args()
     name = args.workload
     wl = dict(WORKLOADS[name])
@@ -260,7 +261,10 @@ def main():
                                                        args.warmup, profile=True)
     value = gb / (ms_step * 1e-3)
     gemm_tflops, gemm_ms, gemm_calls = prof.summary()
-    gemm_stats = torch.tensor([gemm_ms, float(gemm_calls)], device=dev)
+    if args.op_table and rank == 0:
+        Path(args.op_table).parent.mkdir(parents=True, exist_ok=True)
+        Path(args.op_table).write_text(json.dumps({"steps": args.steps, "ms_per_step": ms_step,
+                                                   "rows": prof.table()}, indent=1))
 
     # ---- end-to-end through the public step with HOST buffers (`e2e`) ----
     e2e = None

@@ -433,6 +433,9 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
   return CLIPA_OK;
 }
 
+int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, int H, int causal,
+                     cudaStream_t stream);  // attention_tc.cu
+
 }  // namespace clipa
 
 using namespace clipa;
@@ -443,6 +446,9 @@ extern "C" int clipa_attention_fwd(const void* qkv, void* out, float* lse, int32
   CLIPA_REQUIRE(batch > 0 && L > 0 && heads > 0, CLIPA_ERR_BAD_ARG, "attention_fwd: bad dims");
   CLIPA_REQUIRE((long long)batch * heads < (1LL << 31), CLIPA_ERR_UNSUPPORTED, "attention_fwd: grid too large");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // tcgen05 tile kernel for the shapes every CLIPA pre-training config uses; the mma.sync kernel
+  // covers long sequences (L > 128, e.g. the 224-px fine-tune stage) and other head widths.
+  if (head_dim == 64 && L <= 128) return attention_fwd_tc(qkv, out, lse, batch, L, heads, causal, s);
   switch (head_dim) {
     case 64: return launch_attn_fwd<64>(qkv, out, lse, batch, L, heads, causal, s);
     case 80: return launch_attn_fwd<80>(qkv, out, lse, batch, L, heads, causal, s);

@@ -1,0 +1,552 @@
+// tcgen05 attention forward for CLIPA's short sequences: head_dim 64, L <= 128 (one M=128 tile
+// holds every query of a (sample, head) problem; configs 1, 2, 3, 5 and every text tower).
+//
+// Persistent CTA, 10 warps, two problems in flight:
+//   warp 0      TMA producer: Q, K, V head slices (L rows x 128 B, 128B-swizzled) -> 2-stage smem ring
+//   warp 1      MMA issuer:   S = Q K^T  (tcgen05.mma M128 x N=ceil16(L) x K64, fp32 in TMEM)
+//                             O = P V    (A = P from smem, B = V consumed MN-major in place)
+//   warps 2-5   softmax/epilogue group for even problems   } one thread per query row:
+//   warps 6-9   softmax/epilogue group for odd problems    } tcgen05.ld S row -> mask, max, exp2,
+//                                                            sum -> P (bf16) to swizzled smem;
+//                                                            later tcgen05.ld O row -> 1/l -> 128 B store
+// The score matrix lives only in TMEM/registers; per problem HBM traffic is the algorithmic
+// minimum (Q, K, V read once, O written once).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace clipa {
+
+constexpr int kTcHd = 64;
+constexpr int kTcThreads = 320;
+constexpr int kTcTileBytes = 128 * 128;                     // 128 rows x 128 B
+constexpr int kTcStageBytes = 3 * kTcTileBytes;             // Q, K, V
+constexpr int kTcPBytes = 2 * kTcTileBytes;                 // P: 128 rows x 128 keys bf16 = 2 swizzle atoms
+constexpr int kTcSmemBar = 2 * kTcStageBytes + 2 * kTcPBytes;
+constexpr int kTcSmemTotal = kTcSmemBar + 256 + 1024;
+
+struct AttnTcParams {
+  __nv_bfloat16* out;
+  float* lse;
+  int L, H, batch, causal;
+  int npad;  // ceil16(L)
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* p_base = smem + 2 * kTcStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcSmemBar);
+  uint64_t* full = bars;           // [2] TMA landed
+  uint64_t* kv_empty = bars + 2;   // [2] smem stage free
+  uint64_t* s_full = bars + 4;     // [2] S in TMEM
+  uint64_t* p_full = bars + 6;     // [2] P in smem
+  uint64_t* o_full = bars + 8;     // [2] O in TMEM
+  uint64_t* t_free = bars + 10;    // [2] TMEM stage + P buffer free
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.L, H = p.H, D = H * kTcHd;
+  const int total = p.batch * H;
+
+  // Stale rows [L,128) of the K/V tiles are multiplied by exactly-zero probabilities, so they must
+  // never hold NaN/Inf bit patterns: zero everything once.
+  for (int i = threadIdx.x; i < kTcSmemBar / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&t_free[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // number of problems this CTA owns: blockIdx.x, +gridDim.x, ...
+  const int n_local = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_local; ++i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        const int prob = blockIdx.x + i * gridDim.x;
+        const int n = prob / H, h = prob - n * H;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        uint8_t* st = smem + s * kTcStageBytes;
+        mbar_expect_tx(&full[s], 3u * (uint32_t)L * 128u);
+        tma_load_2d(st, &tmap_qkv, &full[s], h * kTcHd, n * L);
+        tma_load_2d(st + kTcTileBytes, &tmap_qkv, &full[s], D + h * kTcHd, n * L);
+        tma_load_2d(st + 2 * kTcTileBytes, &tmap_qkv, &full[s], 2 * D + h * kTcHd, n * L);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.npad, false, false);
+      const uint32_t idesc_o = make_idesc_bf16(128, kTcHd, false, true);
+      const int ksteps = p.npad / 16;
+      auto issue_pv = [&](int j) {
+        const int sj = j & 1;
+        const uint32_t phj = (j >> 1) & 1;
+        mbar_wait(&p_full[sj], phj);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(p_base + sj * kTcPBytes);
+        const uint32_t va = smem_u32(smem + sj * kTcStageBytes + 2 * kTcTileBytes);
+        const uint32_t d_o = tmem_base + sj * 256 + 128;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(pa + (kk >> 2) * kTcTileBytes + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(va + kk * 2048, 8192, 1024);
+          umma_bf16(d_o, da, db, idesc_o, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[sj]);
+        umma_commit(&kv_empty[sj]);
+      };
+      for (int i = 0; i < n_local; ++i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait(&full[s], ph);
+        mbar_wait(&t_free[s], ph ^ 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(smem + s * kTcStageBytes);
+        const uint32_t ka = qa + kTcTileBytes;
+        const uint32_t d_s = tmem_base + s * 256;
+#pragma unroll
+        for (int k = 0; k < kTcHd / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(qa + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(ka + k * 32, 16, 1024);
+          umma_bf16(d_s, da, db, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[s]);
+        if (i > 0) issue_pv(i - 1);
+      }
+      if (n_local > 0) issue_pv(n_local - 1);
+    }
+  } else {
+    const int grp = (warp - 2) >> 2;  // 0: even problems, 1: odd problems
+    const int q = warp & 3;           // TMEM lane quarter
+    const int row = q * 32 + lane;    // query index handled by this thread
+    uint8_t* pbuf = p_base + grp * kTcPBytes;
+    const uint32_t t_s = tmem_base + grp * 256 + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_o = t_s + 128;
+    for (int i = grp; i < n_local; i += 2) {
+      const uint32_t ph = (i >> 1) & 1;
+      const int prob = blockIdx.x + i * gridDim.x;
+      const int n = prob / H, h = prob - n * H;
+      mbar_wait(&s_full[grp], ph);
+      tc_fence_after();
+      // ---- pass 1: row max over the valid keys
+      float m = -INFINITY;
+      for (int c = 0; c < p.npad; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_s + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int key = c + j;
+          const bool ok = (key < L) && !(p.causal && key > row);
+          m = fmaxf(m, ok ? __uint_as_float(v[j]) : -INFINITY);
+        }
+      }
+      const float ms = (m == -INFINITY) ? 0.f : m * p.scale_log2;
+      // ---- pass 2: P = exp2(s*scale - m), row sum, bf16 P -> swizzled smem (K-major A operand)
+      float l = 0.f;
+      for (int c = 0; c < p.npad; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_s + c, v);
+        tmem_ld_wait();
+        float pr[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int key = c + j;
+          const bool ok = (key < L) && !(p.causal && key > row);
+          pr[j] = ok ? exp2f(__uint_as_float(v[j]) * p.scale_log2 - ms) : 0.f;
+          l += pr[j];
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int chunk = (c >> 3) + g8;  // 16-byte chunk index along the key axis
+          uint4 t;
+          t.x = pack_bf16x2(pr[8 * g8], pr[8 * g8 + 1]);
+          t.y = pack_bf16x2(pr[8 * g8 + 2], pr[8 * g8 + 3]);
+          t.z = pack_bf16x2(pr[8 * g8 + 4], pr[8 * g8 + 5]);
+          t.w = pack_bf16x2(pr[8 * g8 + 6], pr[8 * g8 + 7]);
+          uint8_t* dst = pbuf + (chunk >> 3) * kTcTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = t;
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy P stores -> visible to the MMA (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[grp]);
+      // ---- epilogue: O row / l -> global
+      mbar_wait(&o_full[grp], ph);
+      tc_fence_after();
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(t_o, o0);
+      tmem_ld_32x32(t_o + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_free[grp]);
+      if (row < L) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)n * L + row) * D + h * kTcHd);
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          uint4 t;
+          t.x = pack_bf16x2(__uint_as_float(o0[8 * g8]) * inv, __uint_as_float(o0[8 * g8 + 1]) * inv);
+          t.y = pack_bf16x2(__uint_as_float(o0[8 * g8 + 2]) * inv, __uint_as_float(o0[8 * g8 + 3]) * inv);
+          t.z = pack_bf16x2(__uint_as_float(o0[8 * g8 + 4]) * inv, __uint_as_float(o0[8 * g8 + 5]) * inv);
+          t.w = pack_bf16x2(__uint_as_float(o0[8 * g8 + 6]) * inv, __uint_as_float(o0[8 * g8 + 7]) * inv);
+          dst[g8] = t;
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          uint4 t;
+          t.x = pack_bf16x2(__uint_as_float(o1[8 * g8]) * inv, __uint_as_float(o1[8 * g8 + 1]) * inv);
+          t.y = pack_bf16x2(__uint_as_float(o1[8 * g8 + 2]) * inv, __uint_as_float(o1[8 * g8 + 3]) * inv);
+          t.z = pack_bf16x2(__uint_as_float(o1[8 * g8 + 4]) * inv, __uint_as_float(o1[8 * g8 + 5]) * inv);
+          t.w = pack_bf16x2(__uint_as_float(o1[8 * g8 + 6]) * inv, __uint_as_float(o1[8 * g8 + 7]) * inv);
+          dst[4 + g8] = t;
+        }
+        p.lse[((long long)n * H + h) * L + row] = (ms + log2f(l)) * 0.69314718055994531f;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// host launcher; returns CLIPA_ERR_UNSUPPORTED when the shape is outside this kernel's envelope
+int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, int H, int causal,
+                     cudaStream_t stream) {
+  CLIPA_REQUIRE(L >= 1 && L <= 128, CLIPA_ERR_UNSUPPORTED, "attention_fwd_tc: L=%d > 128", L);
+  const int D = H * kTcHd;
+  CUtensorMap tm;
+  // 2-D view of the packed qkv matrix: inner = 3D columns, outer = batch*L rows; box = 64 cols x L rows
+  int rc = encode_tmap_2d_bf16(&tm, qkv, (uint64_t)3 * D, (uint64_t)batch * L, (uint64_t)3 * D * 2, kTcHd,
+                               (uint32_t)L);
+  if (rc) return rc;
+  AttnTcParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  p.L = L; p.H = H; p.batch = batch; p.causal = causal;
+  p.npad = (L + 15) & ~15;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)kTcHd);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CLIPA_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kTcSmemTotal));
+    attr_set[dev] = true;
+  }
+  long long total = (long long)batch * H;
+  int grid = num_sms();
+  if (grid > total) grid = (int)total;
+  attn_fwd_tc_kernel<<<grid, kTcThreads, kTcSmemTotal, stream>>>(tm, p);
+  CLIPA_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CLIPA_OK;
+}
+
+// ================================================================================================
+// tcgen05 attention backward (head_dim 64, L <= 128).  Per (sample, head), all on M = 128 tiles:
+//   S  = Q K^T          dP = dO V^T                       (both K-major operands)
+//   P  = exp(S*scale - lse),  dS = P o (dP - delta) * scale,  delta_i = sum_d dO_id O_id
+//   dV = P^T dO         dK = dS^T Q                       (A = P / dS consumed MN-major = transposed
+//   dQ = dS K                                              in place; B = dO / Q / K MN-major)
+// P and dS are written once (bf16, 128B-swizzled [query][key] tiles) and serve as the A operand of
+// three MMAs through the descriptor "major" bit -- no transposes, no atomics, no global scratch.
+// TMEM: S 128 + dP 128 + dQ 64 + dK 64 + dV 64 = 448 of 512 columns (one problem in flight per CTA);
+// the Q/K/V/dO smem ring is 2 stages deep so TMA of problem i+1 overlaps the math of problem i.
+//   warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = 8 worker warps: two per TMEM lane
+//   quarter, each owning one half of the columns of a row for the elementwise stage and epilogue.
+// ================================================================================================
+constexpr int kBwStageBytes = 4 * kTcTileBytes;                 // Q, K, V, dO
+constexpr int kBwPOff = 2 * kBwStageBytes;                      // P  (2 atoms)
+constexpr int kBwDsOff = kBwPOff + kTcPBytes;                   // dS (2 atoms)
+constexpr int kBwSmemBar = kBwDsOff + kTcPBytes;
+constexpr int kBwSmemTotal = kBwSmemBar + 256 + 1024;
+
+struct AttnBwParams {
+  const __nv_bfloat16* out;
+  const __nv_bfloat16* dout;
+  const float* lse;
+  __nv_bfloat16* dqkv;
+  int L, H, batch, causal;
+  int npad;
+  float scale;
+};
+
+__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, uint32_t taddr, int col0, bool ok) {
+  // 32 fp32 columns of one TMEM row -> 32 bf16 (64 B) at dst + col0
+  uint32_t v[32];
+  tmem_ld_32x32(taddr + col0, v);
+  tmem_ld_wait();
+  if (ok) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst + col0);
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      uint4 t;
+      t.x = pack_bf16x2(__uint_as_float(v[8 * g8]), __uint_as_float(v[8 * g8 + 1]));
+      t.y = pack_bf16x2(__uint_as_float(v[8 * g8 + 2]), __uint_as_float(v[8 * g8 + 3]));
+      t.z = pack_bf16x2(__uint_as_float(v[8 * g8 + 4]), __uint_as_float(v[8 * g8 + 5]));
+      t.w = pack_bf16x2(__uint_as_float(v[8 * g8 + 6]), __uint_as_float(v[8 * g8 + 7]));
+      d4[g8] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                   const AttnBwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* p_buf = smem + kBwPOff;
+  uint8_t* ds_buf = smem + kBwDsOff;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwSmemBar);
+  uint64_t* full = bars;           // [2] TMA landed
+  uint64_t* kv_empty = bars + 2;   // [2] smem stage free
+  uint64_t* sdp_full = bars + 4;   // S and dP in TMEM
+  uint64_t* pds_full = bars + 5;   // P and dS in smem (8 warp arrivals)
+  uint64_t* grad_full = bars + 6;  // dQ, dK, dV in TMEM
+  uint64_t* t_free = bars + 7;     // TMEM + P/dS buffers free (8 warp arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.L, H = p.H, D = H * kTcHd;
+  const int total = p.batch * H;
+  const long long pitch = 3LL * D;
+
+  for (int i = threadIdx.x; i < kBwSmemBar / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 8);
+    mbar_init(grad_full, 1);
+    mbar_init(t_free, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  constexpr uint32_t kColS = 0, kColDp = 128, kColDq = 256, kColDk = 320, kColDv = 384;
+
+  const int n_local = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_local; ++i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        const int prob = blockIdx.x + i * gridDim.x;
+        const int n = prob / H, h = prob - n * H;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        uint8_t* st = smem + s * kBwStageBytes;
+        mbar_expect_tx(&full[s], 4u * (uint32_t)L * 128u);
+        tma_load_2d(st, &tmap_qkv, &full[s], h * kTcHd, n * L);
+        tma_load_2d(st + kTcTileBytes, &tmap_qkv, &full[s], D + h * kTcHd, n * L);
+        tma_load_2d(st + 2 * kTcTileBytes, &tmap_qkv, &full[s], 2 * D + h * kTcHd, n * L);
+        tma_load_2d(st + 3 * kTcTileBytes, &tmap_do, &full[s], h * kTcHd, n * L);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.npad, false, false);   // A K-major, B K-major
+      const uint32_t idesc_t = make_idesc_bf16(128, kTcHd, true, true);                // A MN (P^T/dS^T), B MN
+      const uint32_t idesc_q = make_idesc_bf16(128, kTcHd, false, true);               // A K (dS), B MN (K)
+      const int ksteps = p.npad / 16;
+      for (int i = 0; i < n_local; ++i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        const uint32_t pi = i & 1;  // phase of the single-stage barriers
+        mbar_wait(&full[s], ph);
+        mbar_wait(t_free, pi ^ 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(smem + s * kBwStageBytes);
+        const uint32_t ka = qa + kTcTileBytes, va = qa + 2 * kTcTileBytes, doa = qa + 3 * kTcTileBytes;
+#pragma unroll
+        for (int k = 0; k < kTcHd / 16; ++k)
+          umma_bf16(tmem_base + kColS, make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                    make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kTcHd / 16; ++k)
+          umma_bf16(tmem_base + kColDp, make_smem_desc_sw128(doa + k * 32, 16, 1024),
+                    make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+        mbar_wait(pds_full, pi);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(p_buf), dsa = smem_u32(ds_buf);
+        for (int kk = 0; kk < ksteps; ++kk) {
+          // contraction over queries: A = P^T / dS^T (MN-major view of the [query][key] tiles:
+          // key atoms 16 KB apart = LBO, 8-query groups 1 KB apart = SBO), B = dO / Q MN-major
+          const uint64_t a_p = make_smem_desc_sw128(pa + kk * 2048, kTcTileBytes, 1024);
+          const uint64_t a_ds = make_smem_desc_sw128(dsa + kk * 2048, kTcTileBytes, 1024);
+          const uint64_t b_do = make_smem_desc_sw128(doa + kk * 2048, 8192, 1024);
+          const uint64_t b_q = make_smem_desc_sw128(qa + kk * 2048, 8192, 1024);
+          umma_bf16(tmem_base + kColDv, a_p, b_do, idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + kColDk, a_ds, b_q, idesc_t, kk > 0 ? 1u : 0u);
+        }
+        for (int kk = 0; kk < ksteps; ++kk) {
+          // contraction over keys: A = dS K-major, B = K MN-major
+          const uint64_t a_ds = make_smem_desc_sw128(dsa + (kk >> 2) * kTcTileBytes + (kk & 3) * 32, 16, 1024);
+          const uint64_t b_k = make_smem_desc_sw128(ka + kk * 2048, 8192, 1024);
+          umma_bf16(tmem_base + kColDq, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(grad_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;     // which half of the columns
+    const int row = q * 32 + lane;        // query index (elementwise stage) / key index (dK, dV rows)
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float scale_log2 = p.scale * 1.4426950408889634f;
+    const int half_cols = p.npad > 64 ? 64 : p.npad;   // columns [half*64, half*64 + 64) of S
+    for (int i = 0; i < n_local; ++i) {
+      const uint32_t pi = i & 1;
+      const int prob = blockIdx.x + i * gridDim.x;
+      const int n = prob / H, h = prob - n * H;
+      // delta_i and lse_i while the MMAs run (global loads, 128 B per thread per tensor)
+      float delta = 0.f, lse2 = 0.f;
+      const bool row_ok = row < L;
+      if (row_ok) {
+        const uint4* orow = reinterpret_cast<const uint4*>(p.out + ((long long)n * L + row) * D + h * kTcHd);
+        const uint4* drow = reinterpret_cast<const uint4*>(p.dout + ((long long)n * L + row) * D + h * kTcHd);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 a = __ldg(orow + c), b = __ldg(drow + c);
+          delta += bf16lo(a.x) * bf16lo(b.x) + bf16hi(a.x) * bf16hi(b.x) + bf16lo(a.y) * bf16lo(b.y) +
+                   bf16hi(a.y) * bf16hi(b.y) + bf16lo(a.z) * bf16lo(b.z) + bf16hi(a.z) * bf16hi(b.z) +
+                   bf16lo(a.w) * bf16lo(b.w) + bf16hi(a.w) * bf16hi(b.w);
+        }
+        lse2 = p.lse[((long long)n * H + h) * L + row] * 1.4426950408889634f;
+      }
+      mbar_wait(sdp_full, pi);
+      tc_fence_after();
+      // columns [c_begin, c_end) of this row
+      const int c_begin = half * 64;
+      const int c_end = min(p.npad, c_begin + 64);
+      for (int c = c_begin; c < c_end; c += 32) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(t_row + kColS + c, sv);
+        tmem_ld_32x32(t_row + kColDp + c, dv);
+        tmem_ld_wait();
+        float pr[32], ds[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int key = c + j;
+          const bool ok = row_ok && (key < L) && !(p.causal && key > row);
+          const float pv = ok ? exp2f(__uint_as_float(sv[j]) * scale_log2 - lse2) : 0.f;
+          pr[j] = pv;
+          ds[j] = pv * (__uint_as_float(dv[j]) - delta) * p.scale;
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int chunk = (c >> 3) + g8;
+          const uint32_t off = (chunk >> 3) * kTcTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+          uint4 t;
+          t.x = pack_bf16x2(pr[8 * g8], pr[8 * g8 + 1]);
+          t.y = pack_bf16x2(pr[8 * g8 + 2], pr[8 * g8 + 3]);
+          t.z = pack_bf16x2(pr[8 * g8 + 4], pr[8 * g8 + 5]);
+          t.w = pack_bf16x2(pr[8 * g8 + 6], pr[8 * g8 + 7]);
+          *reinterpret_cast<uint4*>(p_buf + off) = t;
+          t.x = pack_bf16x2(ds[8 * g8], ds[8 * g8 + 1]);
+          t.y = pack_bf16x2(ds[8 * g8 + 2], ds[8 * g8 + 3]);
+          t.z = pack_bf16x2(ds[8 * g8 + 4], ds[8 * g8 + 5]);
+          t.w = pack_bf16x2(ds[8 * g8 + 6], ds[8 * g8 + 7]);
+          *reinterpret_cast<uint4*>(ds_buf + off) = t;
+        }
+      }
+      (void)half_cols;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      // ---- epilogue: this warp stores 32 of the 64 columns of each gradient row
+      mbar_wait(grad_full, pi);
+      tc_fence_after();
+      __nv_bfloat16* drow = p.dqkv + ((long long)n * L + row) * pitch + h * kTcHd;
+      const int c0 = half * 32;
+      store_row64_bf16(drow, t_row + kColDq, c0, row_ok);              // dQ[row, :]
+      store_row64_bf16(drow + D, t_row + kColDk, c0, row_ok);          // dK[row, :]  (row = key index)
+      store_row64_bf16(drow + 2 * D, t_row + kColDv, c0, row_ok);      // dV[row, :]
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                     int batch, int L, int H, int causal, cudaStream_t stream) {
+  CLIPA_REQUIRE(L >= 1 && L <= 128, CLIPA_ERR_UNSUPPORTED, "attention_bwd_tc: L=%d > 128", L);
+  const int D = H * kTcHd;
+  CUtensorMap tq, td;
+  int rc = encode_tmap_2d_bf16(&tq, qkv, (uint64_t)3 * D, (uint64_t)batch * L, (uint64_t)3 * D * 2, kTcHd,
+                               (uint32_t)L);
+  if (rc) return rc;
+  rc = encode_tmap_2d_bf16(&td, dout, (uint64_t)D, (uint64_t)batch * L, (uint64_t)D * 2, kTcHd, (uint32_t)L);
+  if (rc) return rc;
+  AttnBwParams p;
+  p.out = static_cast<const __nv_bfloat16*>(out);
+  p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.lse = lse;
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.L = L; p.H = H; p.batch = batch; p.causal = causal;
+  p.npad = (L + 15) & ~15;
+  p.scale = 1.0f / sqrtf((float)kTcHd);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CLIPA_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kBwSmemTotal));
+    attr_set[dev] = true;
+  }
+  long long total = (long long)batch * H;
+  int grid = num_sms();
+  if (grid > total) grid = (int)total;
+  attn_bwd_tc_kernel<<<grid, kTcThreads, kBwSmemTotal, stream>>>(tq, td, p);
+  CLIPA_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CLIPA_OK;
+}
+
+}  // namespace clipa

@@ -131,14 +131,26 @@ extern "C" int clipa_gemm(const clipa_gemm_desc* d, void* stream) {
       epi = EPI_ATOMIC_F32;
       CLIPA_REQUIRE(c_f32, CLIPA_ERR_UNSUPPORTED, "gemm: ATOMIC_F32 needs an f32 output");
       int sk = d->split_k;
-      if (sk < 0) {  // auto: aim for ~4 waves of work items, at least 8 k-blocks per item
+      if (sk < 0) {
+        // auto: the smallest split whose work-item count fills whole waves of persistent CTAs
+        // (>= 95 % wave efficiency, >= 2 waves), keeping >= 8 k-blocks per item; every extra split
+        // costs one more pass of fp32 atomics over the output.
         const int BN = (d->N <= 128) ? 128 : 256;
         const long long tiles = (long long)((d->M + kBM - 1) / kBM) * ((d->N + BN - 1) / BN);
         const int kb = (d->K + kBK - 1) / kBK;
-        long long want = (4LL * num_sms() + tiles - 1) / tiles;
-        long long cap = kb / 8 > 0 ? kb / 8 : 1;
-        sk = (int)(want < cap ? want : cap);
-        if (sk < 1) sk = 1;
+        const long long sms = num_sms();
+        int cap = kb / 8 > 0 ? kb / 8 : 1;
+        if (cap > 64) cap = 64;
+        int best = 1;
+        double best_eff = 0.0;
+        for (int s = 1; s <= cap; ++s) {
+          const long long items = tiles * s;
+          const long long waves = (items + sms - 1) / sms;
+          const double eff = (double)items / (double)(waves * sms);
+          if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+          if (eff >= 0.95 && waves >= 2) { best = s; break; }
+        }
+        sk = best;
       }
       p.split_k = sk;
       break;

@@ -19,20 +19,55 @@ ACT_BY_NAME = {"gelu": ACT_GELU_ERF, "gelu_erf": ACT_GELU_ERF, "none": ACT_GELU_
 
 
 class GemmProfiler:
-    """CUDA-event timing of every clipa_gemm launch on the launching stream (bench.py roofline)."""
+    """CUDA-event timing of every kernel launch made through this module, on the launching stream
+    (bench.py roofline).  Records are (key, flops, bytes, start_event, end_event); key[0] is the
+    entry-point name, GEMM keys carry (M, N, K, a_major, b_major, epilogue)."""
 
     def __init__(self):
-        self.records = []  # (flops, start_event, end_event)
+        self.records = []
 
     def summary(self):
-        """-> (achieved TFLOP/s over all timed launches, total ms, number of launches)."""
+        """GEMM launches only -> (achieved TFLOP/s, total ms, number of launches)."""
         torch.cuda.synchronize()
-        ms = sum(s.elapsed_time(e) for _, s, e in self.records)
-        fl = sum(f for f, _, _ in self.records)
-        return (fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0), ms, len(self.records)
+        g = [(f, s.elapsed_time(e)) for k, f, _, s, e in self.records if k[0] == "gemm"]
+        ms = sum(t for _, t in g)
+        fl = sum(f for f, _ in g)
+        return (fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0), ms, len(g)
+
+    def table(self):
+        """Per-key totals: {key: dict(calls, ms, tflops, gbs)} sorted by time."""
+        torch.cuda.synchronize()
+        agg = {}
+        for k, f, b, s, e in self.records:
+            a = agg.setdefault(k, [0, 0.0, 0.0, 0.0])
+            a[0] += 1; a[1] += s.elapsed_time(e); a[2] += f; a[3] += b
+        rows = []
+        for k, (n, ms, f, b) in agg.items():
+            rows.append({"key": list(k), "calls": n, "ms": ms, "tflops": f / (ms * 1e-3) / 1e12 if ms else 0.0,
+                         "gbs": b / (ms * 1e-3) / 1e9 if ms else 0.0})
+        return sorted(rows, key=lambda r: -r["ms"])
 
 
 PROFILER: Optional[GemmProfiler] = None
+
+
+class _prof:
+    """with _prof(key, flops, bytes): <launch>   -- no-op unless a profiler is installed."""
+
+    def __init__(self, key, flops=0.0, nbytes=0.0):
+        self.key, self.flops, self.nbytes = key, flops, nbytes
+
+    def __enter__(self):
+        if PROFILER is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if PROFILER is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILER.records.append((self.key, self.flops, self.nbytes, self.e0, e1))
+        return False
 
 
 def _stream() -> int:
@@ -93,14 +128,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, epilogue: int =
     d.act = act
     d.split_k = split_k
     d.max_ctas = max_ctas
-    if PROFILER is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    with _prof(("gemm", M, N, K, d.a_major, d.b_major, epilogue), 2.0 * M * N * K,
+               2.0 * (M * K + N * K) + out.element_size() * M * N):
         check(_lib.lib().clipa_gemm(C.byref(d), _stream()), "clipa_gemm")
-        e1.record()
-        PROFILER.records.append((2.0 * M * N * K, e0, e1))
-        return out
-    check(_lib.lib().clipa_gemm(C.byref(d), _stream()), "clipa_gemm")
     return out
 
 
@@ -115,8 +145,9 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
     assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
-    check(_lib.lib().clipa_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean),
-                                         _ptr(rstd), rows, D, eps, _stream()), "clipa_layernorm_fwd")
+    with _prof(("ln_fwd", D), 0.0, 4.0 * rows * D):
+        check(_lib.lib().clipa_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean),
+                                             _ptr(rstd), rows, D, eps, _stream()), "clipa_layernorm_fwd")
     return y, mean, rstd
 
 
@@ -126,9 +157,10 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres, dgamma, dbeta):
     rows = x.numel() // D
     assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
     dx = torch.empty_like(x)
-    check(_lib.lib().clipa_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd),
-                                         _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), rows, D,
-                                         _stream()), "clipa_layernorm_bwd")
+    with _prof(("ln_bwd", D), 0.0, (8.0 if dres is not None else 6.0) * rows * D):
+        check(_lib.lib().clipa_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd),
+                                             _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), rows, D,
+                                             _stream()), "clipa_layernorm_bwd")
     return dx
 
 
@@ -139,8 +171,9 @@ def attention_fwd(qkv: torch.Tensor, batch: int, L: int, heads: int, causal: boo
     hd = D // heads
     out = torch.empty(batch * L, D, dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty(batch, heads, L, dtype=torch.float32, device=qkv.device)
-    check(_lib.lib().clipa_attention_fwd(_ptr(qkv), _ptr(out), _ptr(lse), batch, L, heads, hd,
-                                         int(causal), _stream()), "clipa_attention_fwd")
+    with _prof(("attn_fwd", L, hd, int(causal)), 4.0 * batch * heads * L * L * hd, 8.0 * batch * L * D):
+        check(_lib.lib().clipa_attention_fwd(_ptr(qkv), _ptr(out), _ptr(lse), batch, L, heads, hd,
+                                             int(causal), _stream()), "clipa_attention_fwd")
     return out, lse
 
 
@@ -149,17 +182,19 @@ def attention_bwd(qkv, out, dout, lse, batch: int, L: int, heads: int, causal: b
     hd = D // heads
     assert dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
     dqkv = torch.empty_like(qkv)
-    check(_lib.lib().clipa_attention_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
-                                         batch, L, heads, hd, int(causal), _stream()),
-          "clipa_attention_bwd")
+    with _prof(("attn_bwd", L, hd, int(causal)), 10.0 * batch * heads * L * L * hd, 16.0 * batch * L * D):
+        check(_lib.lib().clipa_attention_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
+                                             batch, L, heads, hd, int(causal), _stream()),
+              "clipa_attention_bwd")
     return dqkv
 
 
 def colsum_accum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16
     assert out.dtype == torch.float32 and out.numel() == x.shape[1]
-    check(_lib.lib().clipa_colsum_accum(_ptr(x), x.stride(0), _ptr(out), x.shape[0], x.shape[1],
-                                        _stream()), "clipa_colsum_accum")
+    with _prof(("colsum", x.shape[1]), 0.0, 2.0 * x.shape[0] * x.shape[1]):
+        check(_lib.lib().clipa_colsum_accum(_ptr(x), x.stride(0), _ptr(out), x.shape[0], x.shape[1],
+                                            _stream()), "clipa_colsum_accum")
     return out
 
 
@@ -173,8 +208,9 @@ def clip_lse(a: torch.Tensor, b_all: torch.Tensor, scale: float, label_offset: i
     ws = torch.empty(nws, dtype=torch.float32, device=a.device)
     lse = torch.empty(bl, dtype=torch.float32, device=a.device)
     diag = torch.empty(bl, dtype=torch.float32, device=a.device)
-    check(_lib.lib().clipa_clip_lse(_ptr(a), _ptr(b_all), bl, bg, E, scale, label_offset, _ptr(lse),
-                                    _ptr(diag), _ptr(ws), _stream()), "clipa_clip_lse")
+    with _prof(("clip_lse", bl, bg, E), 2.0 * bl * bg * E, 2.0 * (bl + bg) * E):
+        check(_lib.lib().clipa_clip_lse(_ptr(a), _ptr(b_all), bl, bg, E, scale, label_offset, _ptr(lse),
+                                        _ptr(diag), _ptr(ws), _stream()), "clipa_clip_lse")
     return lse, diag
 
 
@@ -182,8 +218,10 @@ def clip_softmax_grad(a, b_all, scale: float, label_offset: int, lse: torch.Tens
                       dscale_partial: torch.Tensor):
     bl, E = a.shape
     bg = b_all.shape[0]
-    pt = torch.empty(bl, bg, dtype=torch.bfloat16, device=a.device)
-    check(_lib.lib().clipa_clip_softmax_grad(_ptr(a), _ptr(b_all), bl, bg, E, scale, label_offset,
-                                             _ptr(lse), _ptr(pt), pt.stride(0), _ptr(dscale_partial),
-                                             _stream()), "clipa_clip_softmax_grad")
+    ld = (bg + 7) // 8 * 8    # row pitch must stay 16-byte aligned for TMA consumers
+    pt = torch.empty(bl, ld, dtype=torch.bfloat16, device=a.device)[:, :bg]
+    with _prof(("clip_softmax_grad", bl, bg, E), 2.0 * bl * bg * E, 2.0 * (bl + bg) * E + 2.0 * bl * bg):
+        check(_lib.lib().clipa_clip_softmax_grad(_ptr(a), _ptr(b_all), bl, bg, E, scale, label_offset,
+                                                 _ptr(lse), _ptr(pt), pt.stride(0), _ptr(dscale_partial),
+                                                 _stream()), "clipa_clip_softmax_grad")
     return pt

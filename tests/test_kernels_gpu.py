@@ -39,6 +39,8 @@ def mk(shape, dev, scale=1.0, seed=None):
                                    (4096, 3072, 1024)])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
 def test_gemm_majors(dev, M, N, K, a_mn, b_mn):
+    if (a_mn and M % 8) or (b_mn and N % 8) or (not a_mn and K % 8) or (not b_mn and K % 8):
+        pytest.skip("row pitch of an operand would not be 16-byte aligned (rejected by the ABI; see test_gemm_rejects_bad_arguments)")
     torch.manual_seed(M * 7 + N * 3 + K)
     A = mk((K, M), dev).t() if a_mn else mk((M, K), dev)
     B = mk((K, N), dev).t() if b_mn else mk((N, K), dev)
