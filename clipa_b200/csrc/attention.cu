@@ -435,6 +435,8 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
 
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, int H, int causal,
                      cudaStream_t stream);  // attention_tc.cu
+int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                     int batch, int L, int H, int causal, cudaStream_t stream);
 
 }  // namespace clipa
 
@@ -467,6 +469,7 @@ extern "C" int clipa_attention_bwd(const void* qkv, const void* out, const void*
   CLIPA_REQUIRE(batch > 0 && L > 0 && heads > 0, CLIPA_ERR_BAD_ARG, "attention_bwd: bad dims");
   CLIPA_REQUIRE((long long)batch * heads < (1LL << 31), CLIPA_ERR_UNSUPPORTED, "attention_bwd: grid too large");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (head_dim == 64 && L <= 128) return attention_bwd_tc(qkv, out, dout, lse, dqkv, batch, L, heads, causal, s);
   switch (head_dim) {
     case 64: return launch_attn_bwd<64>(qkv, out, dout, lse, dqkv, batch, L, heads, causal, s);
     case 80: return launch_attn_bwd<80>(qkv, out, dout, lse, dqkv, batch, L, heads, causal, s);

@@ -32,6 +32,7 @@ struct AttnTcParams {
   float scale_log2;
 };
 
+template <int NCH>  // 32-column chunks of the score row held in registers: ceil(npad / 32)
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -146,37 +147,37 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
       const int n = prob / H, h = prob - n * H;
       mbar_wait(&s_full[grp], ph);
       tc_fence_after();
-      // ---- pass 1: row max over the valid keys
+      // ---- single TMEM pass: the whole score row (NCH x 32 fp32) is pulled into registers once
+      // (TMEM reads are the scarce resource here: ~64 B/clk/SM), then max -> exp2 -> sum -> bf16 P.
+      uint32_t v[NCH][32];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, v[c]);
+      tmem_ld_wait();
       float m = -INFINITY;
-      for (int c = 0; c < p.npad; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + c, v);
-        tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int key = c + j;
+          const int key = c * 32 + j;
           const bool ok = (key < L) && !(p.causal && key > row);
-          m = fmaxf(m, ok ? __uint_as_float(v[j]) : -INFINITY);
+          m = fmaxf(m, ok ? __uint_as_float(v[c][j]) : -INFINITY);
         }
       }
       const float ms = (m == -INFINITY) ? 0.f : m * p.scale_log2;
-      // ---- pass 2: P = exp2(s*scale - m), row sum, bf16 P -> swizzled smem (K-major A operand)
       float l = 0.f;
-      for (int c = 0; c < p.npad; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_s + c, v);
-        tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         float pr[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int key = c + j;
+          const int key = c * 32 + j;
           const bool ok = (key < L) && !(p.causal && key > row);
-          pr[j] = ok ? exp2f(__uint_as_float(v[j]) * p.scale_log2 - ms) : 0.f;
+          pr[j] = ok ? exp2f(fmaf(__uint_as_float(v[c][j]), p.scale_log2, -ms)) : 0.f;
           l += pr[j];
         }
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-          const int chunk = (c >> 3) + g8;  // 16-byte chunk index along the key axis
+          const int chunk = c * 4 + g8;  // 16-byte chunk index along the key axis
           uint4 t;
           t.x = pack_bf16x2(pr[8 * g8], pr[8 * g8 + 1]);
           t.y = pack_bf16x2(pr[8 * g8 + 2], pr[8 * g8 + 3]);
@@ -250,18 +251,23 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, i
   p.L = L; p.H = H; p.batch = batch; p.causal = causal;
   p.npad = (L + 15) & ~15;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)kTcHd);
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  CLIPA_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && !attr_set[dev]) {
-    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kTcSmemTotal));
-    attr_set[dev] = true;
-  }
   long long total = (long long)batch * H;
   int grid = num_sms();
   if (grid > total) grid = (int)total;
-  attn_fwd_tc_kernel<<<grid, kTcThreads, kTcSmemTotal, stream>>>(tm, p);
+  const int nch = (p.npad + 31) / 32;
+  auto launch = [&](auto kern) -> int {
+    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemTotal));
+    kern<<<grid, kTcThreads, kTcSmemTotal, stream>>>(tm, p);
+    return CLIPA_OK;
+  };
+  int lrc;
+  switch (nch) {
+    case 1: lrc = launch(attn_fwd_tc_kernel<1>); break;
+    case 2: lrc = launch(attn_fwd_tc_kernel<2>); break;
+    case 3: lrc = launch(attn_fwd_tc_kernel<3>); break;
+    default: lrc = launch(attn_fwd_tc_kernel<4>); break;
+  }
+  if (lrc) return lrc;
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CLIPA_OK;
@@ -431,7 +437,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const int row = q * 32 + lane;        // query index (elementwise stage) / key index (dK, dV rows)
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float scale_log2 = p.scale * 1.4426950408889634f;
-    const int half_cols = p.npad > 64 ? 64 : p.npad;   // columns [half*64, half*64 + 64) of S
     for (int i = 0; i < n_local; ++i) {
       const uint32_t pi = i & 1;
       const int prob = blockIdx.x + i * gridDim.x;
@@ -487,7 +492,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           *reinterpret_cast<uint4*>(ds_buf + off) = t;
         }
       }
-      (void)half_cols;
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();

@@ -68,29 +68,60 @@ struct GemmSmem {
 // ------------------------------------------------------------------------------------------------
 // activation math (fp32)
 // ------------------------------------------------------------------------------------------------
+// erf-GELU uses the Abramowitz-Stegun 7.1.26 rational/exponential form of erf
+// (|error| <= 1.5e-7, i.e. fp32 round-off; far below the bf16 output resolution): one MUFU.RCP,
+// one MUFU.EX2 and a 5-term Horner chain per element instead of libdevice erff -- with libdevice
+// the epilogue warps, not the tensor pipe, paced the c_fc GEMM (417 TFLOP/s measured, round 1).
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// returns erf(|x|/sqrt2) in `erf_abs` and exp(-x^2/2) in `e`
+__device__ __forceinline__ void erf_half_core(float x, float& erf_abs, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  e = exp2f(-z * z * 1.4426950408889634f);
+  erf_abs = fmaf(-poly, e, 1.0f);
+}
 __device__ __forceinline__ float act_fwd(float x, int act) {
-  if (act == 0) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
-  if (act == 1) {
-    float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-    return 0.5f * x * (1.0f + tanhf(u));
+  if (act == 0) {
+    float ea, e;
+    erf_half_core(x, ea, e);
+    return 0.5f * x * (1.0f + copysignf(ea, x));
   }
-  return x / (1.0f + __expf(-1.702f * x));
+  if (act == 1) {
+    const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+    return 0.5f * x * (1.0f + fast_tanh(u));
+  }
+  return x * fast_rcp(1.0f + exp2f(-1.702f * 1.4426950408889634f * x));
 }
 __device__ __forceinline__ float act_bwd(float x, int act) {
   if (act == 0) {
-    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-    float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    float ea, e;
+    erf_half_core(x, ea, e);
+    const float cdf = 0.5f * (1.0f + copysignf(ea, x));
+    return fmaf(x * 0.3989422804014327f, e, cdf);
   }
   if (act == 1) {
-    float x2 = x * x;
-    float u = 0.7978845608028654f * (x + 0.044715f * x * x2);
-    float t = tanhf(u);
-    float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x2);
+    const float x2 = x * x;
+    const float u = 0.7978845608028654f * fmaf(0.044715f * x2, x, x);
+    const float t = fast_tanh(u);
+    const float du = 0.7978845608028654f * fmaf(3.0f * 0.044715f, x2, 1.0f);
     return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
   }
-  float s = 1.0f / (1.0f + __expf(-1.702f * x));
-  return s * (1.0f + 1.702f * x * (1.0f - s));
+  const float sg = fast_rcp(1.0f + exp2f(-1.702f * 1.4426950408889634f * x));
+  return sg * (1.0f + 1.702f * x * (1.0f - sg));
 }
 
 __device__ __forceinline__ void load_bias32(const void* bias, int bias_f32, int col0, float (&b)[32]) {
@@ -323,18 +354,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
+        const uint32_t t_warp = tmem_base + acc * BN + half * kColsPerWarp + (static_cast<uint32_t>(q * 32) << 16);
+        uint32_t vnext[32];
+        tmem_ld_32x32(t_warp, vnext);
 #pragma unroll 1
         for (int c = 0; c < kColsPerWarp / 32; ++c) {
           const int col_local = half * kColsPerWarp + c * 32;
           const int col0 = n_blk * BN + col_local;
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + acc * BN + col_local + (static_cast<uint32_t>(q * 32) << 16), v);
-          tmem_ld_wait();
+          float f[32];
+          tmem_ld_wait_regs(vnext);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vnext[j]);
+          if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32(t_warp + (c + 1) * 32, vnext);  // prefetch next chunk
           if (col0 >= p.N) continue;  // warp-uniform
           const bool full = (col0 + 32 <= p.N);
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
 
           if constexpr (EPI == EPI_STORE) {
 #pragma unroll
@@ -385,16 +418,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
               }
+              if (p.act == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], p.act);
+                for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 0);
+              } else if (p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 1);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 2);
+              }
               store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
             }
           } else if constexpr (EPI == EPI_DACT) {
             if (row_ok) {
               float a[32];
               load_bf16x32(p.aux + row * p.ldaux + col0, a);
+              if (p.act == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], p.act);
+                for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 0);
+              } else if (p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 1);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 2);
+              }
               store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
             }
           } else if constexpr (EPI == EPI_ATOMIC_F32) {

@@ -96,15 +96,19 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 //   dx = rstd * (g - mean_D(g) - xhat * mean_D(g*xhat)) (+ dres)
 //   dgamma += sum_rows dy*xhat ;  dbeta += sum_rows dy
 // Each warp keeps its dgamma/dbeta partials in registers over its grid-stride rows; the block
-// reduces them through shared memory and issues one red.add per column per block.
+// reduces them through shared memory and issues one red.add per column per block.  To keep the
+// register footprint low enough for 2 blocks/SM the row is held PACKED (bf16x2) between the
+// statistics pass and the output pass, and gamma is read from shared memory.
 template <int VPL>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, 2)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
               __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
               long long rows, int D) {
-  extern __shared__ float red[];  // [kLnWarps][2][D]
+  extern __shared__ float red[];  // [D] gamma, then [kLnWarps][2][D] reduction scratch
+  float* sgam = red;
+  float* scratch = red + D;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nvec = D >> 3;
@@ -112,19 +116,14 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   const long long warp_stride = (long long)gridDim.x * kLnWarps;
   const float inv_d = 1.0f / (float)D;
 
-  float gam[VPL][8];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) sgam[c] = gamma[c];
+  __syncthreads();
+
   float acc_g[VPL][8], acc_b[VPL][8];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + 32 * i;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc_g[i][j] = 0.f; acc_b[i][j] = 0.f; gam[i][j] = 0.f; }
-    if (vi < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
-      gam[i][0] = g0.x; gam[i][1] = g0.y; gam[i][2] = g0.z; gam[i][3] = g0.w;
-      gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
-    }
+    for (int j = 0; j < 8; ++j) { acc_g[i][j] = 0.f; acc_b[i][j] = 0.f; }
   }
 
   for (long long row = warp_global; row < rows; row += warp_stride) {
@@ -132,22 +131,33 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + row * D);
     const float mean = mean_in[row];
     const float rstd = rstd_in[row];
-    float xh[VPL][8], g[VPL][8];
+    uint4 xp[VPL], dp[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
+        xp[i] = __ldg(xr + vi);
+        dp[i] = __ldg(dyr + vi);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
         float xv[8], dv[8];
-        unpack8(__ldg(xr + vi), xv);
-        unpack8(__ldg(dyr + vi), dv);
+        unpack8(xp[i], xv);
+        unpack8(dp[i], dv);
+        const float4 g0 = *reinterpret_cast<const float4*>(sgam + vi * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(sgam + vi * 8 + 4);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mean) * rstd;
-          g[i][j] = dv[j] * gam[i][j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-          acc_g[i][j] += dv[j] * xh[i][j];
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = dv[j] * gm[j];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          acc_g[i][j] = fmaf(dv[j], xh, acc_g[i][j]);
           acc_b[i][j] += dv[j];
         }
       }
@@ -159,9 +169,17 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        float o[8];
+        float xv[8], dv[8], o[8];
+        unpack8(xp[i], xv);
+        unpack8(dp[i], dv);
+        const float4 g0 = *reinterpret_cast<const float4*>(sgam + vi * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(sgam + vi * 8 + 4);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          o[j] = rstd * (dv[j] * gm[j] - s1 - xh * s2);
+        }
         if (dres) {
           float r[8];
           unpack8(__ldg(reinterpret_cast<const uint4*>(dres + row * D) + vi), r);
@@ -174,7 +192,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   }
 
   // block reduction of the parameter-gradient partials
-  float* my_g = red + (size_t)warp * 2 * D;
+  float* my_g = scratch + (size_t)warp * 2 * D;
   float* my_b = my_g + D;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
@@ -192,8 +210,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     float sg = 0.f, sb = 0.f;
 #pragma unroll
     for (int w = 0; w < kLnWarps; ++w) {
-      sg += red[(size_t)w * 2 * D + c];
-      sb += red[(size_t)w * 2 * D + D + c];
+      sg += scratch[(size_t)w * 2 * D + c];
+      sb += scratch[(size_t)w * 2 * D + D + c];
     }
     atomicAdd(dgamma + c, sg);
     atomicAdd(dbeta + c, sb);
@@ -250,9 +268,9 @@ static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const
                          const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
                          long long rows, int D, cudaStream_t s) {
   long long blocks = (rows + kLnWarps - 1) / kLnWarps;
-  const long long cap = (long long)num_sms() * 4;
+  const long long cap = (long long)num_sms() * 2;
   if (blocks > cap) blocks = cap;
-  const size_t smem = (size_t)kLnWarps * 2 * D * sizeof(float);
+  const size_t smem = ((size_t)kLnWarps * 2 + 1) * D * sizeof(float);
   auto kern = ln_bwd_kernel<VPL>;
   if (smem > 48 * 1024)
     CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
