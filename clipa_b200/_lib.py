@@ -49,6 +49,7 @@ _SIGNATURES = {
     "clipa_last_error": (C.c_char_p, []),
     "clipa_launch_count": (C.c_int64, []),
     "clipa_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "clipa_set_gemm_mode": (C.c_int, [C.c_int]),
     "clipa_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
     "clipa_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

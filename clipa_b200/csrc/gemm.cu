@@ -1,5 +1,6 @@
 // Host launcher + C ABI for the tcgen05 GEMM family (see gemm_tc.cuh for the kernel).
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "host_common.h"
 
 namespace clipa {
@@ -22,12 +23,78 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return CLIPA_OK;
 }
 
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                        cudaStream_t stream) {
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, EPI>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CLIPA_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal2));
+    attr_set[dev] = true;
+  }
+  kern<<<grid, kGemmThreads, kSmemTotal2, stream>>>(ta, tb, p);
+  CLIPA_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CLIPA_OK;
+}
+
+// 2-CTA path: 256 x 256 pair tiles (each CTA: 128 rows of A, 128 of the 256 B rows per stage).
+static int gemm_dispatch_2cta(GemmParams p, const void* A, long long lda, bool a_mn, const void* B,
+                              long long ldb, bool b_mn, int epi, int max_ctas, cudaStream_t stream) {
+  p.m_blocks = (p.M + 2 * kBM - 1) / (2 * kBM);
+  p.n_blocks = (p.N + kBN2 - 1) / kBN2;
+  p.k_blocks = (p.K + kBK - 1) / kBK;
+  p.n_per_chunk = 1;
+  p.n_chunks = p.n_blocks;
+  if (p.split_k < 1) p.split_k = 1;
+  if (p.split_k > p.k_blocks) p.split_k = p.k_blocks;
+  p.kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
+  p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+  p.num_items = p.split_k * p.m_blocks * p.n_blocks;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = encode_tmap_2d_bf16(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, kBK, kBM);
+  else       rc = encode_tmap_2d_bf16(&ta, A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda * 2, 64, kBK);
+  if (rc) return rc;
+  if (!b_mn) rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldb * 2, kBK, kBN2 / 2);
+  else       rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb * 2, 64, kBK);
+  if (rc) return rc;
+  int clusters = num_sms() / 2;
+  if (max_ctas > 1 && max_ctas / 2 < clusters) clusters = max_ctas / 2;
+  if (clusters > p.num_items) clusters = p.num_items;
+  const int grid = clusters * 2;
+#define CLIPA_GEMM2_CASE(AMN_, BMN_, EPI_) \
+  if (a_mn == AMN_ && b_mn == BMN_ && epi == EPI_) return launch_gemm2<AMN_, BMN_, EPI_>(ta, tb, p, grid, stream);
+  CLIPA_GEMM2_CASE(false, false, EPI_STORE)
+  CLIPA_GEMM2_CASE(false, true, EPI_STORE)
+  CLIPA_GEMM2_CASE(true, true, EPI_STORE)
+  CLIPA_GEMM2_CASE(true, false, EPI_STORE)
+  CLIPA_GEMM2_CASE(false, false, EPI_BIAS_ACT)
+  CLIPA_GEMM2_CASE(false, true, EPI_DACT)
+  CLIPA_GEMM2_CASE(true, true, EPI_ATOMIC_F32)
+  CLIPA_GEMM2_CASE(false, false, EPI_ATOMIC_F32)
+  CLIPA_GEMM2_CASE(false, true, EPI_ATOMIC_F32)
+  CLIPA_GEMM2_CASE(true, false, EPI_ATOMIC_F32)
+#undef CLIPA_GEMM2_CASE
+  return 1;  // not built for this combination -> caller falls back to the 1-CTA kernel
+}
+
+// 0 = auto (2-CTA when the problem is big enough), 1 = force 1-CTA, 2 = force 2-CTA (tests)
+static int g_gemm_mode = 0;
+
 // Builds tensor maps and derived tiling, then dispatches on (BN, majors, epilogue).
 int gemm_dispatch(GemmParams p, const void* A, long long lda, bool a_mn, const void* B,
                   long long ldb, bool b_mn, int epi, int max_ctas, cudaStream_t stream) {
   CLIPA_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, CLIPA_ERR_BAD_ARG, "gemm: M,N,K must be positive (%d,%d,%d)",
                 p.M, p.N, p.K);
   CLIPA_REQUIRE(A && B, CLIPA_ERR_BAD_ARG, "gemm: null operand");
+  if (epi <= EPI_ATOMIC_F32 && g_gemm_mode != 1 &&
+      (g_gemm_mode == 2 || (p.M >= 1024 && p.N >= 256))) {
+    const int rc2 = gemm_dispatch_2cta(p, A, lda, a_mn, B, ldb, b_mn, epi, max_ctas, stream);
+    if (rc2 <= 0) return rc2;
+  }
   const int BN = (p.N <= 128) ? 128 : 256;
   p.m_blocks = (p.M + kBM - 1) / kBM;
   p.n_blocks = (p.N + BN - 1) / BN;
@@ -81,6 +148,12 @@ int gemm_dispatch(GemmParams p, const void* A, long long lda, bool a_mn, const v
 }  // namespace clipa
 
 using namespace clipa;
+
+extern "C" int clipa_set_gemm_mode(int mode) {
+  CLIPA_REQUIRE(mode >= 0 && mode <= 2, CLIPA_ERR_BAD_ARG, "set_gemm_mode: mode must be 0 (auto), 1 (1-CTA) or 2 (2-CTA)");
+  g_gemm_mode = mode;
+  return CLIPA_OK;
+}
 
 extern "C" int clipa_gemm(const clipa_gemm_desc* d, void* stream) {
   CLIPA_REQUIRE(d != nullptr, CLIPA_ERR_BAD_ARG, "gemm: null descriptor");
@@ -136,9 +209,11 @@ extern "C" int clipa_gemm(const clipa_gemm_desc* d, void* stream) {
         // (>= 95 % wave efficiency, >= 2 waves), keeping >= 8 k-blocks per item; every extra split
         // costs one more pass of fp32 atomics over the output.
         const int BN = (d->N <= 128) ? 128 : 256;
-        const long long tiles = (long long)((d->M + kBM - 1) / kBM) * ((d->N + BN - 1) / BN);
+        const bool pair = g_gemm_mode != 1 && (g_gemm_mode == 2 || (d->M >= 1024 && d->N >= 256));
+        const long long tiles = pair ? (long long)((d->M + 2 * kBM - 1) / (2 * kBM)) * ((d->N + kBN2 - 1) / kBN2)
+                                     : (long long)((d->M + kBM - 1) / kBM) * ((d->N + BN - 1) / BN);
         const int kb = (d->K + kBK - 1) / kBK;
-        const long long sms = num_sms();
+        const long long sms = pair ? num_sms() / 2 : num_sms();
         int cap = kb / 8 > 0 ? kb / 8 : 1;
         if (cap > 64) cap = 64;
         int best = 1;

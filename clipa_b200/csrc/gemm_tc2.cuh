@@ -1,0 +1,337 @@
+// 2-CTA (cta_group::2) variant of the persistent tcgen05 GEMM: a CTA pair (cluster of 2 on one TPC)
+// computes a 256 x 256 output tile.  Each CTA stages its own 128 rows of A and HALF of the B tile
+// (128 of the 256 N-rows); the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), the hardware
+// reads the other half of B from the peer's shared memory.  Per MMA-FLOP this cuts the
+// L2 -> shared-memory traffic by a third (32 KB instead of 48 KB per 128x256x64 MACs per CTA) --
+// the 1-CTA kernel is L2-feed-bound at ~95 B/clk/SM -- and deepens the ring to 6 stages.
+//
+//   warp 0 (both CTAs): TMA producer for the CTA's own A / B-half tiles; completion is signalled on
+//                       the LEADER's full barrier (cp.async.bulk.tensor ... .cta_group::2)
+//   warp 1 (leader)   : MMA issuer; tcgen05.commit.multicast releases smem stages / publishes
+//                       accumulators in BOTH CTAs
+//   warps 2..9 (both) : epilogue on the CTA's own 128 TMEM lanes (rows r*128.. of the pair tile);
+//                       accumulator-drained arrivals go to the leader's tmem_empty barrier
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace clipa {
+
+constexpr int kBN2 = 256;          // pair tile N
+constexpr int kStages2 = 6;
+constexpr int kABytes2 = kBM * kBK * 2;        // 128 x 64 bf16
+constexpr int kBBytes2 = (kBN2 / 2) * kBK * 2; // this CTA's half of B
+constexpr int kStageBytes2 = kABytes2 + kBBytes2;
+constexpr int kBarOffset2 = kStages2 * kStageBytes2;
+constexpr int kSmemTotal2 = kBarOffset2 + 256 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in the LEADER (even) CTA of the pair: within a CTA
+// pair the peer is selected by bit 24 of the shared-window address; clearing it targets rank 0.
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local_smem_addr) { return local_smem_addr & 0xFEFFFFFFu; }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose mbarrier may live in the peer CTA (cluster address)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr,
+                                                int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once) on the barrier at this offset in BOTH CTAs of the pair when prior MMAs retire
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+// The four store-type epilogues on one 32-column chunk of one output row (shared by both kernels).
+template <int EPI>
+__device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[32], long long row, bool row_ok,
+                                                int col0) {
+  const bool full = (col0 + 32 <= p.N);
+  if constexpr (EPI == EPI_STORE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+    if (full) {
+      if (p.bias) {
+        float b[32];
+        load_bias32(p.bias, p.bias_f32, col0, b);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] += b[j];
+      }
+      if (row_ok) {
+        if (p.residual) {
+          float rr[32];
+          load_bf16x32(p.residual + row * p.ldr + col0, rr);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += rr[j];
+        }
+        if (p.c_f32) store_f32x32(static_cast<float*>(p.C) + row * p.ldc + col0, f);
+        else store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+      }
+    } else if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + j;
+        if (col < p.N) {
+          float x = f[j];
+          if (p.bias) x += load_bias1(p.bias, p.bias_f32, col);
+          if (p.residual) x += __bfloat162float(p.residual[row * p.ldr + col]);
+          if (p.c_f32) static_cast<float*>(p.C)[row * p.ldc + col] = x;
+          else static_cast<__nv_bfloat16*>(p.C)[row * p.ldc + col] = __float2bfloat16(x);
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_BIAS_ACT) {
+    if (p.bias) {
+      float b[32];
+      load_bias32(p.bias, p.bias_f32, col0, b);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] += b[j];
+    }
+    if (row_ok) {
+      if (p.aux) {
+        store_bf16x32(p.aux + row * p.ldaux + col0, f);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
+      }
+      if (p.act == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 0);
+      } else if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 2);
+      }
+      store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+    }
+  } else if constexpr (EPI == EPI_DACT) {
+    if (row_ok) {
+      float a[32];
+      load_bf16x32(p.aux + row * p.ldaux + col0, a);
+      if (p.act == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 0);
+      } else if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 2);
+      }
+      store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+    }
+  } else if constexpr (EPI == EPI_ATOMIC_F32) {
+    if (row_ok) {
+      float* dst = static_cast<float*>(p.C) + row * p.ldc + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          red_add_f32x4(dst + j, p.alpha * f[j], p.alpha * f[j + 1], p.alpha * f[j + 2], p.alpha * f[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) atomicAdd(dst + j, p.alpha * f[j]);
+      }
+    }
+  }
+}
+
+// GemmParams here: m_blocks counts 256-row PAIR tiles, n_blocks counts 256-column tiles.
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const GemmParams p) {
+  constexpr uint32_t kTmemCols = 2 * kBN2;
+  constexpr uint32_t kIdesc = make_idesc_bf16(2 * kBM, kBN2, A_MN, B_MN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOffset2);   // used in the leader
+  uint64_t* empty_bar = full_bar + kStages2;                              // per CTA
+  uint64_t* tmem_full = empty_bar + kStages2;                             // per CTA
+  uint64_t* tmem_empty = tmem_full + 2;                                   // used in the leader
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kNumEpiWarps);  // epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int items_mn = p.m_blocks * p.n_blocks;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ======================= TMA producer (both CTAs) =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < p.num_items; w += num_clusters) {
+        const int split = w / items_mn;
+        const int r = w - split * items_mn;
+        const int m_blk = r / p.n_blocks;
+        const int n_blk = r - m_blk * p.n_blocks;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(p.k_blocks, kb_begin + p.kb_per_split);
+        const int m0 = m_blk * (2 * kBM) + (int)rank * kBM;        // this CTA's 128 rows of A
+        const int n0 = n_blk * kBN2 + (int)rank * (kBN2 / 2);       // this CTA's half of B
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes2;
+          uint8_t* sb = sa + kABytes2;
+          const uint32_t full_leader = leader_addr(smem_u32(&full_bar[stage]));
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(sa, &tmap_a, full_leader, kb * kBK, m0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < kBM / 64; ++a)
+              tma_load_2d_2sm(sa + a * (kBK * 128), &tmap_a, full_leader, m0 + a * 64, kb * kBK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(sb, &tmap_b, full_leader, kb * kBK, n0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < (kBN2 / 2) / 64; ++a)
+              tma_load_2d_2sm(sb + a * (kBK * 128), &tmap_b, full_leader, n0 + a * 64, kb * kBK);
+          }
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader CTA only) =======================
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = cluster_id; w < p.num_items; w += num_clusters) {
+        const int split = w / items_mn;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(p.k_blocks, kb_begin + p.kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + acc * kBN2;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes2);
+          const uint32_t sb = sa + kABytes2;
+          const uint64_t da = A_MN ? make_smem_desc_sw128(sa, kBK * 128, 1024) : make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc_sw128(sb, kBK * 128, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+          constexpr uint32_t a_step = (A_MN ? 2048 : 32) >> 4;
+          constexpr uint32_t b_step = (B_MN ? 2048 : 32) >> 4;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16_2sm(d_addr, da + static_cast<uint64_t>(k * a_step), db + static_cast<uint64_t>(k * b_step),
+                          kIdesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ======================= epilogue warps (both CTAs) =======================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    constexpr int kColsPerWarp = kBN2 / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = cluster_id; w < p.num_items; w += num_clusters) {
+      const int split = w / items_mn;
+      const int r = w - split * items_mn;
+      const int m_blk = r / p.n_blocks;
+      const int n_blk = r - m_blk * p.n_blocks;
+      const long long row = (long long)m_blk * (2 * kBM) + (long long)rank * kBM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_warp = tmem_base + acc * kBN2 + half * kColsPerWarp + (static_cast<uint32_t>(q * 32) << 16);
+      uint32_t vnext[32];
+      tmem_ld_32x32(t_warp, vnext);
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp / 32; ++c) {
+        const int col0 = n_blk * kBN2 + half * kColsPerWarp + c * 32;
+        float f[32];
+        tmem_ld_wait_regs(vnext);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vnext[j]);
+        if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32(t_warp + (c + 1) * 32, vnext);
+        if (col0 >= p.N) continue;
+        epi_apply_store<EPI>(p, f, row, row_ok, col0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_addr(smem_u32(&tmem_empty[acc])));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // teardown: nobody may exit (or free TMEM) while the peer can still touch this CTA's smem/TMEM
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace clipa

@@ -86,6 +86,10 @@ int64_t clipa_launch_count(void);
  *   `pooled @ self.proj`, `x @ self.text_projection`  transformer.py:529, model.py:254-260
  * and their autograd backward (dgrad: B MN-major; wgrad: A and B MN-major, split-K atomic). */
 int clipa_gemm(const clipa_gemm_desc* desc, void* stream);
+/* Kernel selection for clipa_gemm: 0 = auto (2-CTA cta_group::2 pair tiles for large problems),
+ * 1 = always the 1-CTA kernel, 2 = always the 2-CTA kernel where it is built.  Process-wide; meant
+ * for tests and A/B measurements. */
+int clipa_set_gemm_mode(int mode);
 
 /* ---- LayerNorm ------------------------------------------------------------------------------
  * F.layer_norm via LayerNorm/LayerNormFp32 (open_clip/transformer.py:19-34): fp32 statistics,

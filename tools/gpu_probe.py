@@ -250,6 +250,11 @@ def group_gemm_perf():
 
 
 if __name__ == "__main__":
+    import os
+    from clipa_b200 import _lib
+    mode = int(os.environ.get("CLIPA_GEMM_MODE", "0"))
+    _lib.check(_lib.lib().clipa_set_gemm_mode(mode), "set_gemm_mode")
+    print(f"gemm mode {mode}", flush=True)
     g = sys.argv[1]
     t0 = time.time()
     globals()["group_" + g]()
