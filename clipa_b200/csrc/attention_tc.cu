@@ -1,13 +1,14 @@
-// tcgen05 attention forward for CLIPA's short sequences: head_dim 64, L <= 128 (one M=128 tile
-// holds every query of a (sample, head) problem; configs 1, 2, 3, 5 and every text tower).
+// tcgen05 attention for CLIPA's short sequences: head_dim 64, L <= 128 (one M=128 tile holds every
+// query of a (sample, head) problem; configs 1, 2, 3, 5 and every text tower).  The mma.sync kernels
+// in attention.cu cover longer sequences and other head widths.
 //
-// Persistent CTA, 10 warps, two problems in flight:
+// FORWARD -- persistent CTA, 10 warps, two problems in flight:
 //   warp 0      TMA producer: Q, K, V head slices (L rows x 128 B, 128B-swizzled) -> 2-stage smem ring
 //   warp 1      MMA issuer:   S = Q K^T  (tcgen05.mma M128 x N=ceil16(L) x K64, fp32 in TMEM)
 //                             O = P V    (A = P from smem, B = V consumed MN-major in place)
 //   warps 2-5   softmax/epilogue group for even problems   } one thread per query row:
-//   warps 6-9   softmax/epilogue group for odd problems    } tcgen05.ld S row -> mask, max, exp2,
-//                                                            sum -> P (bf16) to swizzled smem;
+//   warps 6-9   softmax/epilogue group for odd problems    } tcgen05.ld S row (once) -> mask, max,
+//                                                            exp2, sum -> P (bf16) to swizzled smem;
 //                                                            later tcgen05.ld O row -> 1/l -> 128 B store
 // The score matrix lives only in TMEM/registers; per problem HBM traffic is the algorithmic
 // minimum (Q, K, V read once, O written once).
@@ -27,12 +28,31 @@ constexpr int kTcSmemTotal = kTcSmemBar + 256 + 1024;
 struct AttnTcParams {
   __nv_bfloat16* out;
   float* lse;
-  int L, H, batch, causal;
+  int L, H, batch;
   int npad;  // ceil16(L)
   float scale_log2;
 };
 
-template <int NCH>  // 32-column chunks of the score row held in registers: ceil(npad / 32)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float* f) {
+  uint4 t;
+  t.x = pack_bf16x2(f[0], f[1]);
+  t.y = pack_bf16x2(f[2], f[3]);
+  t.z = pack_bf16x2(f[4], f[5]);
+  t.w = pack_bf16x2(f[6], f[7]);
+  return t;
+}
+// byte offset of 16-byte chunk `chunk` (along the key axis) of row `row` in a [128 x 128-key] bf16
+// tile stored as two 128B-swizzled atoms of 64 keys
+__device__ __forceinline__ uint32_t p_tile_off(int row, int chunk) {
+  return (chunk >> 3) * kTcTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+}
+
+template <int NCH, bool CAUSAL>  // NCH = 32-column chunks of the score row held in registers
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -138,6 +158,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
     const int grp = (warp - 2) >> 2;  // 0: even problems, 1: odd problems
     const int q = warp & 3;           // TMEM lane quarter
     const int row = q * 32 + lane;    // query index handled by this thread
+    const bool warp_has_rows = q * 32 < L;  // warp-uniform: all 32 rows beyond L -> nothing to compute
     uint8_t* pbuf = p_base + grp * kTcPBytes;
     const uint32_t t_s = tmem_base + grp * 256 + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t t_o = t_s + 128;
@@ -147,82 +168,76 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
       const int n = prob / H, h = prob - n * H;
       mbar_wait(&s_full[grp], ph);
       tc_fence_after();
-      // ---- single TMEM pass: the whole score row (NCH x 32 fp32) is pulled into registers once
-      // (TMEM reads are the scarce resource here: ~64 B/clk/SM), then max -> exp2 -> sum -> bf16 P.
-      uint32_t v[NCH][32];
+      float l = 0.f, ms = 0.f;
+      if (warp_has_rows) {
+        // ---- single TMEM pass: the whole score row (NCH x 32 fp32) is pulled into registers once
+        // (TMEM reads are the scarce resource: ~64 B/clk/SM), then max -> exp2 -> sum -> bf16 P.
+        uint32_t v[NCH][32];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, v[c]);
-      tmem_ld_wait();
-      float m = -INFINITY;
+        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, v[c]);
+        tmem_ld_wait();
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
+        for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = c * 32 + j;
-          const bool ok = (key < L) && !(p.causal && key > row);
-          m = fmaxf(m, ok ? __uint_as_float(v[c][j]) : -INFINITY);
+          for (int j = 0; j < 32; ++j) {
+            const int key = c * 32 + j;
+            float x = __uint_as_float(v[c][j]);
+            if (key >= L || (CAUSAL && key > row)) x = -INFINITY;
+            v[c][j] = __float_as_uint(x);
+            mx[j & 3] = fmaxf(mx[j & 3], x);
+          }
         }
+        const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        ms = (m == -INFINITY) ? 0.f : m * p.scale_log2;
+        float sm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float pr[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            pr[j] = ex2_approx(fmaf(__uint_as_float(v[c][j]), p.scale_log2, -ms));  // exp2(-inf) = 0
+            sm[j & 3] += pr[j];
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8)
+            *reinterpret_cast<uint4*>(pbuf + p_tile_off(row, c * 4 + g8)) = pack8_bf16(pr + 8 * g8);
+        }
+        l = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+        fence_proxy_async_smem();  // generic-proxy P stores -> visible to the MMA (async proxy)
       }
-      const float ms = (m == -INFINITY) ? 0.f : m * p.scale_log2;
-      float l = 0.f;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        float pr[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = c * 32 + j;
-          const bool ok = (key < L) && !(p.causal && key > row);
-          pr[j] = ok ? exp2f(fmaf(__uint_as_float(v[c][j]), p.scale_log2, -ms)) : 0.f;
-          l += pr[j];
-        }
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int chunk = c * 4 + g8;  // 16-byte chunk index along the key axis
-          uint4 t;
-          t.x = pack_bf16x2(pr[8 * g8], pr[8 * g8 + 1]);
-          t.y = pack_bf16x2(pr[8 * g8 + 2], pr[8 * g8 + 3]);
-          t.z = pack_bf16x2(pr[8 * g8 + 4], pr[8 * g8 + 5]);
-          t.w = pack_bf16x2(pr[8 * g8 + 6], pr[8 * g8 + 7]);
-          uint8_t* dst = pbuf + (chunk >> 3) * kTcTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = t;
-        }
-      }
-      fence_proxy_async_smem();  // generic-proxy P stores -> visible to the MMA (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[grp]);
       // ---- epilogue: O row / l -> global
       mbar_wait(&o_full[grp], ph);
       tc_fence_after();
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32(t_o, o0);
-      tmem_ld_32x32(t_o + 32, o1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_free[grp]);
-      if (row < L) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)n * L + row) * D + h * kTcHd);
+      if (warp_has_rows) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(t_o, o0);
+        tmem_ld_32x32(t_o + 32, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_free[grp]);
+        if (row < L) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)n * L + row) * D + h * kTcHd);
+          float f[32];
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          uint4 t;
-          t.x = pack_bf16x2(__uint_as_float(o0[8 * g8]) * inv, __uint_as_float(o0[8 * g8 + 1]) * inv);
-          t.y = pack_bf16x2(__uint_as_float(o0[8 * g8 + 2]) * inv, __uint_as_float(o0[8 * g8 + 3]) * inv);
-          t.z = pack_bf16x2(__uint_as_float(o0[8 * g8 + 4]) * inv, __uint_as_float(o0[8 * g8 + 5]) * inv);
-          t.w = pack_bf16x2(__uint_as_float(o0[8 * g8 + 6]) * inv, __uint_as_float(o0[8 * g8 + 7]) * inv);
-          dst[g8] = t;
-        }
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(o0[j]) * inv;
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          uint4 t;
-          t.x = pack_bf16x2(__uint_as_float(o1[8 * g8]) * inv, __uint_as_float(o1[8 * g8 + 1]) * inv);
-          t.y = pack_bf16x2(__uint_as_float(o1[8 * g8 + 2]) * inv, __uint_as_float(o1[8 * g8 + 3]) * inv);
-          t.z = pack_bf16x2(__uint_as_float(o1[8 * g8 + 4]) * inv, __uint_as_float(o1[8 * g8 + 5]) * inv);
-          t.w = pack_bf16x2(__uint_as_float(o1[8 * g8 + 6]) * inv, __uint_as_float(o1[8 * g8 + 7]) * inv);
-          dst[4 + g8] = t;
+          for (int g8 = 0; g8 < 4; ++g8) dst[g8] = pack8_bf16(f + 8 * g8);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(o1[j]) * inv;
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) dst[4 + g8] = pack8_bf16(f + 8 * g8);
+          p.lse[((long long)n * H + h) * L + row] = (ms + log2f(l)) * 0.69314718055994531f;
         }
-        p.lse[((long long)n * H + h) * L + row] = (ms + log2f(l)) * 0.69314718055994531f;
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_free[grp]);
       }
     }
   }
@@ -248,7 +263,7 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, i
   AttnTcParams p;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
-  p.L = L; p.H = H; p.batch = batch; p.causal = causal;
+  p.L = L; p.H = H; p.batch = batch;
   p.npad = (L + 15) & ~15;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)kTcHd);
   long long total = (long long)batch * H;
@@ -261,11 +276,20 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, i
     return CLIPA_OK;
   };
   int lrc;
-  switch (nch) {
-    case 1: lrc = launch(attn_fwd_tc_kernel<1>); break;
-    case 2: lrc = launch(attn_fwd_tc_kernel<2>); break;
-    case 3: lrc = launch(attn_fwd_tc_kernel<3>); break;
-    default: lrc = launch(attn_fwd_tc_kernel<4>); break;
+  if (causal) {
+    switch (nch) {
+      case 1: lrc = launch(attn_fwd_tc_kernel<1, true>); break;
+      case 2: lrc = launch(attn_fwd_tc_kernel<2, true>); break;
+      case 3: lrc = launch(attn_fwd_tc_kernel<3, true>); break;
+      default: lrc = launch(attn_fwd_tc_kernel<4, true>); break;
+    }
+  } else {
+    switch (nch) {
+      case 1: lrc = launch(attn_fwd_tc_kernel<1, false>); break;
+      case 2: lrc = launch(attn_fwd_tc_kernel<2, false>); break;
+      case 3: lrc = launch(attn_fwd_tc_kernel<3, false>); break;
+      default: lrc = launch(attn_fwd_tc_kernel<4, false>); break;
+    }
   }
   if (lrc) return lrc;
   CLIPA_CHECK_CUDA(cudaGetLastError());
@@ -274,7 +298,7 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, i
 }
 
 // ================================================================================================
-// tcgen05 attention backward (head_dim 64, L <= 128).  Per (sample, head), all on M = 128 tiles:
+// BACKWARD (head_dim 64, L <= 128).  Per (sample, head), all on M = 128 tiles:
 //   S  = Q K^T          dP = dO V^T                       (both K-major operands)
 //   P  = exp(S*scale - lse),  dS = P o (dP - delta) * scale,  delta_i = sum_d dO_id O_id
 //   dV = P^T dO         dK = dS^T Q                       (A = P / dS consumed MN-major = transposed
@@ -282,48 +306,46 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, i
 // P and dS are written once (bf16, 128B-swizzled [query][key] tiles) and serve as the A operand of
 // three MMAs through the descriptor "major" bit -- no transposes, no atomics, no global scratch.
 // TMEM: S 128 + dP 128 + dQ 64 + dK 64 + dV 64 = 448 of 512 columns (one problem in flight per CTA);
-// the Q/K/V/dO smem ring is 2 stages deep so TMA of problem i+1 overlaps the math of problem i.
+// the Q/K/V/dO/O smem ring is 2 stages deep so TMA of problem i+1 overlaps the math of problem i
+// (O rides the ring too: delta is computed from shared memory, no global-load latency per problem).
 //   warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = 8 worker warps: two per TMEM lane
 //   quarter, each owning one half of the columns of a row for the elementwise stage and epilogue.
 // ================================================================================================
-constexpr int kBwStageBytes = 4 * kTcTileBytes;                 // Q, K, V, dO
+constexpr int kBwTiles = 5;                                      // Q, K, V, dO, O
+constexpr int kBwStageBytes = kBwTiles * kTcTileBytes;
 constexpr int kBwPOff = 2 * kBwStageBytes;                      // P  (2 atoms)
 constexpr int kBwDsOff = kBwPOff + kTcPBytes;                   // dS (2 atoms)
 constexpr int kBwSmemBar = kBwDsOff + kTcPBytes;
 constexpr int kBwSmemTotal = kBwSmemBar + 256 + 1024;
+static_assert(kBwSmemTotal <= 227 * 1024, "attention backward shared memory budget");
 
 struct AttnBwParams {
-  const __nv_bfloat16* out;
-  const __nv_bfloat16* dout;
   const float* lse;
   __nv_bfloat16* dqkv;
-  int L, H, batch, causal;
+  int L, H, batch;
   int npad;
   float scale;
 };
 
-__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, uint32_t taddr, int col0, bool ok) {
-  // 32 fp32 columns of one TMEM row -> 32 bf16 (64 B) at dst + col0
+// 32 fp32 columns of one TMEM row -> 32 bf16 (64 B) at dst + col0
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, uint32_t taddr, int col0, bool ok) {
   uint32_t v[32];
   tmem_ld_32x32(taddr + col0, v);
   tmem_ld_wait();
   if (ok) {
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
     uint4* d4 = reinterpret_cast<uint4*>(dst + col0);
 #pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {
-      uint4 t;
-      t.x = pack_bf16x2(__uint_as_float(v[8 * g8]), __uint_as_float(v[8 * g8 + 1]));
-      t.y = pack_bf16x2(__uint_as_float(v[8 * g8 + 2]), __uint_as_float(v[8 * g8 + 3]));
-      t.z = pack_bf16x2(__uint_as_float(v[8 * g8 + 4]), __uint_as_float(v[8 * g8 + 5]));
-      t.w = pack_bf16x2(__uint_as_float(v[8 * g8 + 6]), __uint_as_float(v[8 * g8 + 7]));
-      d4[g8] = t;
-    }
+    for (int g8 = 0; g8 < 4; ++g8) d4[g8] = pack8_bf16(f + 8 * g8);
   }
 }
 
+template <bool CAUSAL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                   const AttnBwParams p) {
+                   const __grid_constant__ CUtensorMap tmap_o, const AttnBwParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -349,6 +371,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_o);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&kv_empty[i], 1);
@@ -377,11 +400,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         const int n = prob / H, h = prob - n * H;
         mbar_wait(&kv_empty[s], ph ^ 1);
         uint8_t* st = smem + s * kBwStageBytes;
-        mbar_expect_tx(&full[s], 4u * (uint32_t)L * 128u);
+        mbar_expect_tx(&full[s], (uint32_t)kBwTiles * (uint32_t)L * 128u);
         tma_load_2d(st, &tmap_qkv, &full[s], h * kTcHd, n * L);
         tma_load_2d(st + kTcTileBytes, &tmap_qkv, &full[s], D + h * kTcHd, n * L);
         tma_load_2d(st + 2 * kTcTileBytes, &tmap_qkv, &full[s], 2 * D + h * kTcHd, n * L);
         tma_load_2d(st + 3 * kTcTileBytes, &tmap_do, &full[s], h * kTcHd, n * L);
+        tma_load_2d(st + 4 * kTcTileBytes, &tmap_o, &full[s], h * kTcHd, n * L);
       }
     }
   } else if (warp == 1) {
@@ -435,75 +459,85 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;     // which half of the columns
     const int row = q * 32 + lane;        // query index (elementwise stage) / key index (dK, dV rows)
+    const bool row_ok = row < L;
+    const bool warp_writes = q * 32 < p.npad;  // rows >= npad are never contracted: skip their P/dS
+    const bool warp_stores = q * 32 < L;       // rows >= L have no gradient rows to store
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float scale_log2 = p.scale * 1.4426950408889634f;
+    const int c_begin = half * 64;
+    const int c_end = min(p.npad, c_begin + 64);
+    float lse2_next = 0.f;
+    if (n_local > 0 && row_ok) {
+      const int prob0 = blockIdx.x;
+      lse2_next = p.lse[(long long)prob0 * L + row] * 1.4426950408889634f;   // lse is [batch, H, L]
+    }
     for (int i = 0; i < n_local; ++i) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
       const uint32_t pi = i & 1;
       const int prob = blockIdx.x + i * gridDim.x;
       const int n = prob / H, h = prob - n * H;
-      // delta_i and lse_i while the MMAs run (global loads, 128 B per thread per tensor)
-      float delta = 0.f, lse2 = 0.f;
-      const bool row_ok = row < L;
-      if (row_ok) {
-        const uint4* orow = reinterpret_cast<const uint4*>(p.out + ((long long)n * L + row) * D + h * kTcHd);
-        const uint4* drow = reinterpret_cast<const uint4*>(p.dout + ((long long)n * L + row) * D + h * kTcHd);
+      const float lse2 = lse2_next;
+      if (i + 1 < n_local && row_ok)  // prefetch the next problem's lse (one float per thread)
+        lse2_next = p.lse[(long long)(prob + (int)gridDim.x) * L + row] * 1.4426950408889634f;
+      // delta_i = sum_d dO_id * O_id from the swizzled smem tiles (TMA already landed them)
+      mbar_wait(&full[s], ph);
+      float delta = 0.f;
+      if (row_ok && c_begin < c_end) {
+        const uint8_t* dot = smem + s * kBwStageBytes + 3 * kTcTileBytes + row * 128;
+        const uint8_t* ot = dot + kTcTileBytes;
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const uint4 a = __ldg(orow + c), b = __ldg(drow + c);
-          delta += bf16lo(a.x) * bf16lo(b.x) + bf16hi(a.x) * bf16hi(b.x) + bf16lo(a.y) * bf16lo(b.y) +
-                   bf16hi(a.y) * bf16hi(b.y) + bf16lo(a.z) * bf16lo(b.z) + bf16hi(a.z) * bf16hi(b.z) +
-                   bf16lo(a.w) * bf16lo(b.w) + bf16hi(a.w) * bf16hi(b.w);
+          const uint32_t off = ((c ^ (row & 7)) << 4);
+          const uint4 a = *reinterpret_cast<const uint4*>(ot + off);
+          const uint4 b = *reinterpret_cast<const uint4*>(dot + off);
+          d4[0] = fmaf(bf16lo(a.x), bf16lo(b.x), fmaf(bf16hi(a.x), bf16hi(b.x), d4[0]));
+          d4[1] = fmaf(bf16lo(a.y), bf16lo(b.y), fmaf(bf16hi(a.y), bf16hi(b.y), d4[1]));
+          d4[2] = fmaf(bf16lo(a.z), bf16lo(b.z), fmaf(bf16hi(a.z), bf16hi(b.z), d4[2]));
+          d4[3] = fmaf(bf16lo(a.w), bf16lo(b.w), fmaf(bf16hi(a.w), bf16hi(b.w), d4[3]));
         }
-        lse2 = p.lse[((long long)n * H + h) * L + row] * 1.4426950408889634f;
+        delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
       }
       mbar_wait(sdp_full, pi);
       tc_fence_after();
-      // columns [c_begin, c_end) of this row
-      const int c_begin = half * 64;
-      const int c_end = min(p.npad, c_begin + 64);
-      for (int c = c_begin; c < c_end; c += 32) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(t_row + kColS + c, sv);
-        tmem_ld_32x32(t_row + kColDp + c, dv);
-        tmem_ld_wait();
-        float pr[32], ds[32];
+      if (warp_writes) {
+        for (int c = c_begin; c < c_end; c += 32) {
+          uint32_t sv[32], dv[32];
+          tmem_ld_32x32(t_row + kColS + c, sv);
+          tmem_ld_32x32(t_row + kColDp + c, dv);
+          tmem_ld_wait();
+          float pr[32], ds[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = c + j;
-          const bool ok = row_ok && (key < L) && !(p.causal && key > row);
-          const float pv = ok ? exp2f(__uint_as_float(sv[j]) * scale_log2 - lse2) : 0.f;
-          pr[j] = pv;
-          ds[j] = pv * (__uint_as_float(dv[j]) - delta) * p.scale;
-        }
+          for (int j = 0; j < 32; ++j) {
+            const int key = c + j;
+            const bool ok = row_ok && (key < L) && !(CAUSAL && key > row);
+            const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[j]), scale_log2, -lse2)) : 0.f;
+            pr[j] = pv;
+            ds[j] = pv * (__uint_as_float(dv[j]) - delta) * p.scale;
+          }
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int chunk = (c >> 3) + g8;
-          const uint32_t off = (chunk >> 3) * kTcTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
-          uint4 t;
-          t.x = pack_bf16x2(pr[8 * g8], pr[8 * g8 + 1]);
-          t.y = pack_bf16x2(pr[8 * g8 + 2], pr[8 * g8 + 3]);
-          t.z = pack_bf16x2(pr[8 * g8 + 4], pr[8 * g8 + 5]);
-          t.w = pack_bf16x2(pr[8 * g8 + 6], pr[8 * g8 + 7]);
-          *reinterpret_cast<uint4*>(p_buf + off) = t;
-          t.x = pack_bf16x2(ds[8 * g8], ds[8 * g8 + 1]);
-          t.y = pack_bf16x2(ds[8 * g8 + 2], ds[8 * g8 + 3]);
-          t.z = pack_bf16x2(ds[8 * g8 + 4], ds[8 * g8 + 5]);
-          t.w = pack_bf16x2(ds[8 * g8 + 6], ds[8 * g8 + 7]);
-          *reinterpret_cast<uint4*>(ds_buf + off) = t;
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const uint32_t off = p_tile_off(row, (c >> 3) + g8);
+            *reinterpret_cast<uint4*>(p_buf + off) = pack8_bf16(pr + 8 * g8);
+            *reinterpret_cast<uint4*>(ds_buf + off) = pack8_bf16(ds + 8 * g8);
+          }
         }
+        fence_proxy_async_smem();
       }
-      fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
       // ---- epilogue: this warp stores 32 of the 64 columns of each gradient row
       mbar_wait(grad_full, pi);
       tc_fence_after();
-      __nv_bfloat16* drow = p.dqkv + ((long long)n * L + row) * pitch + h * kTcHd;
-      const int c0 = half * 32;
-      store_row64_bf16(drow, t_row + kColDq, c0, row_ok);              // dQ[row, :]
-      store_row64_bf16(drow + D, t_row + kColDk, c0, row_ok);          // dK[row, :]  (row = key index)
-      store_row64_bf16(drow + 2 * D, t_row + kColDv, c0, row_ok);      // dV[row, :]
+      if (warp_stores) {
+        __nv_bfloat16* drow = p.dqkv + ((long long)n * L + row) * pitch + h * kTcHd;
+        const int c0 = half * 32;
+        store_row32_bf16(drow, t_row + kColDq, c0, row_ok);              // dQ[row, :]
+        store_row32_bf16(drow + D, t_row + kColDk, c0, row_ok);          // dK[row, :]  (row = key index)
+        store_row32_bf16(drow + 2 * D, t_row + kColDv, c0, row_ok);      // dV[row, :]
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_free);
@@ -522,32 +556,30 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const f
                      int batch, int L, int H, int causal, cudaStream_t stream) {
   CLIPA_REQUIRE(L >= 1 && L <= 128, CLIPA_ERR_UNSUPPORTED, "attention_bwd_tc: L=%d > 128", L);
   const int D = H * kTcHd;
-  CUtensorMap tq, td;
+  CUtensorMap tq, td, to;
   int rc = encode_tmap_2d_bf16(&tq, qkv, (uint64_t)3 * D, (uint64_t)batch * L, (uint64_t)3 * D * 2, kTcHd,
                                (uint32_t)L);
   if (rc) return rc;
   rc = encode_tmap_2d_bf16(&td, dout, (uint64_t)D, (uint64_t)batch * L, (uint64_t)D * 2, kTcHd, (uint32_t)L);
   if (rc) return rc;
+  rc = encode_tmap_2d_bf16(&to, out, (uint64_t)D, (uint64_t)batch * L, (uint64_t)D * 2, kTcHd, (uint32_t)L);
+  if (rc) return rc;
   AttnBwParams p;
-  p.out = static_cast<const __nv_bfloat16*>(out);
-  p.dout = static_cast<const __nv_bfloat16*>(dout);
   p.lse = lse;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
-  p.L = L; p.H = H; p.batch = batch; p.causal = causal;
+  p.L = L; p.H = H; p.batch = batch;
   p.npad = (L + 15) & ~15;
   p.scale = 1.0f / sqrtf((float)kTcHd);
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  CLIPA_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && !attr_set[dev]) {
-    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kBwSmemTotal));
-    attr_set[dev] = true;
-  }
   long long total = (long long)batch * H;
   int grid = num_sms();
   if (grid > total) grid = (int)total;
-  attn_bwd_tc_kernel<<<grid, kTcThreads, kBwSmemTotal, stream>>>(tq, td, p);
+  auto launch = [&](auto kern) -> int {
+    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwSmemTotal));
+    kern<<<grid, kTcThreads, kBwSmemTotal, stream>>>(tq, td, to, p);
+    return CLIPA_OK;
+  };
+  const int lrc = causal ? launch(attn_bwd_tc_kernel<true>) : launch(attn_bwd_tc_kernel<false>);
+  if (lrc) return lrc;
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CLIPA_OK;

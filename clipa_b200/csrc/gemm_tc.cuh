@@ -62,7 +62,8 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+  static constexpr int kBiasOffset = kBarOffset + 256;   // 2 x 256 fp32 bias slices (per accumulator stage)
+  static constexpr int kTotal = kBiasOffset + 2048 + 1024;  // + alignment slack
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -180,6 +181,179 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
                "f"(d)
                : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// The four store-type epilogues on one 32-column chunk of one output row (shared by the 1-CTA and
+// 2-CTA kernels).  `sb` = this chunk's 32 bias values in shared memory (staged once per tile, so no
+// global-load latency sits on the per-chunk critical path); `side` = the chunk's residual (STORE) or
+// saved pre-activation (DACT) row segment, prefetched one chunk ahead by the caller.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack_bf16x32(const uint4 (&s)[4], float (&r)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r[8 * i] = bf16lo(s[i].x); r[8 * i + 1] = bf16hi(s[i].x);
+    r[8 * i + 2] = bf16lo(s[i].y); r[8 * i + 3] = bf16hi(s[i].y);
+    r[8 * i + 4] = bf16lo(s[i].z); r[8 * i + 5] = bf16hi(s[i].z);
+    r[8 * i + 6] = bf16lo(s[i].w); r[8 * i + 7] = bf16hi(s[i].w);
+  }
+}
+template <int EPI>
+__device__ __forceinline__ const __nv_bfloat16* epi_side_ptr(const GemmParams& p, long long& ld) {
+  if constexpr (EPI == EPI_STORE) { ld = p.ldr; return p.residual; }
+  if constexpr (EPI == EPI_DACT) { ld = p.ldaux; return p.aux; }
+  ld = 0;
+  return nullptr;
+}
+template <int EPI>
+__device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[32], long long row, bool row_ok,
+                                                int col0, const float* sb, const uint4 (&side)[4]) {
+  const bool full = (col0 + 32 <= p.N);
+  if constexpr (EPI == EPI_STORE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(sb + j);
+        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+      }
+    }
+    if (full) {
+      if (row_ok) {
+        if (p.residual) {
+          float rr[32];
+          unpack_bf16x32(side, rr);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += rr[j];
+        }
+        if (p.c_f32) store_f32x32(static_cast<float*>(p.C) + row * p.ldc + col0, f);
+        else store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+      }
+    } else if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + j;
+        if (col < p.N) {
+          float x = f[j];
+          if (p.residual) x += __bfloat162float(p.residual[row * p.ldr + col]);
+          if (p.c_f32) static_cast<float*>(p.C)[row * p.ldc + col] = x;
+          else static_cast<__nv_bfloat16*>(p.C)[row * p.ldc + col] = __float2bfloat16(x);
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_BIAS_ACT) {
+    // requires N % 32 == 0 (checked on the host)
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(sb + j);
+        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+      }
+    }
+    if (row_ok) {
+      if (p.aux) {
+        // the pre-activation is stored in bf16 and the activation is evaluated on the ROUNDED
+        // value, so backward (which re-reads aux) sees the same operand
+        store_bf16x32(p.aux + row * p.ldaux + col0, f);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
+      }
+      if (p.act == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 0);
+      } else if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 2);
+      }
+      store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+    }
+  } else if constexpr (EPI == EPI_DACT) {
+    if (row_ok) {
+      float a[32];
+      unpack_bf16x32(side, a);
+      if (p.act == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 0);
+      } else if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 2);
+      }
+      store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+    }
+  } else if constexpr (EPI == EPI_ATOMIC_F32) {
+    if (row_ok) {
+      float* dst = static_cast<float*>(p.C) + row * p.ldc + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          red_add_f32x4(dst + j, p.alpha * f[j], p.alpha * f[j + 1], p.alpha * f[j + 2], p.alpha * f[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) atomicAdd(dst + j, p.alpha * f[j]);
+      }
+    }
+  }
+}
+
+// One accumulator stage's worth of store-type epilogue for one warp: `ncols` columns starting at
+// tile-local column `col_local0`; TMEM loads and the side-operand loads run one chunk ahead.
+template <int EPI>
+__device__ __forceinline__ void epi_run_store(const GemmParams& p, uint32_t t_warp, long long row, bool row_ok,
+                                              int tile_col0, int col_local0, int ncols, const float* sbias_tile) {
+  long long side_ld;
+  const __nv_bfloat16* side_base = epi_side_ptr<EPI>(p, side_ld);
+  const bool use_side = side_base != nullptr && row_ok;
+  uint4 side_next[4] = {};
+  uint32_t vnext[32];
+  tmem_ld_32x32(t_warp, vnext);
+  {
+    const int col0 = tile_col0 + col_local0;
+    if (use_side && col0 + 32 <= p.N) {
+      const uint4* q = reinterpret_cast<const uint4*>(side_base + row * side_ld + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) side_next[i] = __ldg(q + i);
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < ncols / 32; ++c) {
+    const int col0 = tile_col0 + col_local0 + c * 32;
+    float f[32];
+    uint4 side[4];
+    tmem_ld_wait_regs(vnext);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vnext[j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) side[i] = side_next[i];
+    if (c + 1 < ncols / 32) {
+      tmem_ld_32x32(t_warp + (c + 1) * 32, vnext);
+      const int coln = col0 + 32;
+      if (use_side && coln + 32 <= p.N) {
+        const uint4* q = reinterpret_cast<const uint4*>(side_base + row * side_ld + coln);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) side_next[i] = __ldg(q + i);
+      }
+    }
+    if (col0 >= p.N) continue;  // warp-uniform
+    epi_apply_store<EPI>(p, f, row, row_ok, col0, sbias_tile + col_local0 + c * 32, side);
+  }
+}
+
+// Stage the tile's bias slice (fp32) in shared memory: one value per epilogue thread.
+__device__ __forceinline__ void epi_stage_bias(const GemmParams& p, float* sbias_tile, int tile_col0, int bn) {
+  const int t = threadIdx.x - 64;  // epilogue threads are 64..319
+  if (p.bias && t < bn) {
+    const int col = tile_col0 + t;
+    sbias_tile[t] = col < p.N ? load_bias1(p.bias, p.bias_f32, col) : 0.f;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kNumEpiWarps) : "memory");
 }
 
 // Per-thread (= per output row) running state of the contrastive-head LSE epilogue.
@@ -352,9 +526,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int label = row + p.label_offset;
 
       for (int n_blk = n_begin; n_blk < n_end; ++n_blk) {
+        float* sbias_tile = reinterpret_cast<float*>(smem + S::kBiasOffset) + acc * 256;
+        if constexpr (EPI <= EPI_ATOMIC_F32) epi_stage_bias(p, sbias_tile, n_blk * BN, BN);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_warp = tmem_base + acc * BN + half * kColsPerWarp + (static_cast<uint32_t>(q * 32) << 16);
+        if constexpr (EPI <= EPI_ATOMIC_F32) {
+          epi_run_store<EPI>(p, t_warp, row, row_ok, n_blk * BN, half * kColsPerWarp, kColsPerWarp, sbias_tile);
+        } else {
         uint32_t vnext[32];
         tmem_ld_32x32(t_warp, vnext);
 #pragma unroll 1
@@ -369,98 +548,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (col0 >= p.N) continue;  // warp-uniform
           const bool full = (col0 + 32 <= p.N);
 
-          if constexpr (EPI == EPI_STORE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
-            if (full) {
-              if (p.bias) {
-                float b[32];
-                load_bias32(p.bias, p.bias_f32, col0, b);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] += b[j];
-              }
-              if (row_ok) {
-                if (p.residual) {
-                  float rr[32];
-                  load_bf16x32(p.residual + row * p.ldr + col0, rr);
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) f[j] += rr[j];
-                }
-                if (p.c_f32) store_f32x32(static_cast<float*>(p.C) + row * p.ldc + col0, f);
-                else store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
-              }
-            } else if (row_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int col = col0 + j;
-                if (col < p.N) {
-                  float x = f[j];
-                  if (p.bias) x += load_bias1(p.bias, p.bias_f32, col);
-                  if (p.residual) x += __bfloat162float(p.residual[row * p.ldr + col]);
-                  if (p.c_f32) static_cast<float*>(p.C)[row * p.ldc + col] = x;
-                  else static_cast<__nv_bfloat16*>(p.C)[row * p.ldc + col] = __float2bfloat16(x);
-                }
-              }
-            }
-          } else if constexpr (EPI == EPI_BIAS_ACT) {
-            // requires N % 32 == 0 (checked on the host)
-            if (p.bias) {
-              float b[32];
-              load_bias32(p.bias, p.bias_f32, col0, b);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += b[j];
-            }
-            if (row_ok) {
-              if (p.aux) {
-                // the pre-activation is stored in bf16 and the activation is evaluated on the
-                // ROUNDED value, so backward (which re-reads aux) sees the same operand
-                store_bf16x32(p.aux + row * p.ldaux + col0, f);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
-              }
-              if (p.act == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 0);
-              } else if (p.act == 1) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 1);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 2);
-              }
-              store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
-            }
-          } else if constexpr (EPI == EPI_DACT) {
-            if (row_ok) {
-              float a[32];
-              load_bf16x32(p.aux + row * p.ldaux + col0, a);
-              if (p.act == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 0);
-              } else if (p.act == 1) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 1);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 2);
-              }
-              store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
-            }
-          } else if constexpr (EPI == EPI_ATOMIC_F32) {
-            if (row_ok) {
-              float* dst = static_cast<float*>(p.C) + row * p.ldc + col0;
-              if (full) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  red_add_f32x4(dst + j, p.alpha * f[j], p.alpha * f[j + 1], p.alpha * f[j + 2],
-                                p.alpha * f[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) atomicAdd(dst + j, p.alpha * f[j]);
-              }
-            }
-          } else if constexpr (EPI == EPI_LSE) {
+          if constexpr (EPI == EPI_LSE) {
             // t = logit * log2(e); online (max, sum 2^(t-max)) per row
             float gmax = -INFINITY;
 #pragma unroll
@@ -499,6 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
+        }  // contrastive-head epilogues
         // all of this warp's TMEM reads for the stage are complete (wait::ld above)
         tc_fence_before();
         __syncwarp();

@@ -22,7 +22,8 @@ constexpr int kABytes2 = kBM * kBK * 2;        // 128 x 64 bf16
 constexpr int kBBytes2 = (kBN2 / 2) * kBK * 2; // this CTA's half of B
 constexpr int kStageBytes2 = kABytes2 + kBBytes2;
 constexpr int kBarOffset2 = kStages2 * kStageBytes2;
-constexpr int kSmemTotal2 = kBarOffset2 + 256 + 1024;
+constexpr int kBiasOffset2 = kBarOffset2 + 256;
+constexpr int kSmemTotal2 = kBiasOffset2 + 2048 + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -73,101 +74,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
       : "memory");
-}
-
-// The four store-type epilogues on one 32-column chunk of one output row (shared by both kernels).
-template <int EPI>
-__device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[32], long long row, bool row_ok,
-                                                int col0) {
-  const bool full = (col0 + 32 <= p.N);
-  if constexpr (EPI == EPI_STORE) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
-    if (full) {
-      if (p.bias) {
-        float b[32];
-        load_bias32(p.bias, p.bias_f32, col0, b);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] += b[j];
-      }
-      if (row_ok) {
-        if (p.residual) {
-          float rr[32];
-          load_bf16x32(p.residual + row * p.ldr + col0, rr);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += rr[j];
-        }
-        if (p.c_f32) store_f32x32(static_cast<float*>(p.C) + row * p.ldc + col0, f);
-        else store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
-      }
-    } else if (row_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = col0 + j;
-        if (col < p.N) {
-          float x = f[j];
-          if (p.bias) x += load_bias1(p.bias, p.bias_f32, col);
-          if (p.residual) x += __bfloat162float(p.residual[row * p.ldr + col]);
-          if (p.c_f32) static_cast<float*>(p.C)[row * p.ldc + col] = x;
-          else static_cast<__nv_bfloat16*>(p.C)[row * p.ldc + col] = __float2bfloat16(x);
-        }
-      }
-    }
-  } else if constexpr (EPI == EPI_BIAS_ACT) {
-    if (p.bias) {
-      float b[32];
-      load_bias32(p.bias, p.bias_f32, col0, b);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] += b[j];
-    }
-    if (row_ok) {
-      if (p.aux) {
-        store_bf16x32(p.aux + row * p.ldaux + col0, f);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
-      }
-      if (p.act == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 0);
-      } else if (p.act == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 1);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 2);
-      }
-      store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
-    }
-  } else if constexpr (EPI == EPI_DACT) {
-    if (row_ok) {
-      float a[32];
-      load_bf16x32(p.aux + row * p.ldaux + col0, a);
-      if (p.act == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 0);
-      } else if (p.act == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 1);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 2);
-      }
-      store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
-    }
-  } else if constexpr (EPI == EPI_ATOMIC_F32) {
-    if (row_ok) {
-      float* dst = static_cast<float*>(p.C) + row * p.ldc + col0;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          red_add_f32x4(dst + j, p.alpha * f[j], p.alpha * f[j + 1], p.alpha * f[j + 2], p.alpha * f[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) atomicAdd(dst + j, p.alpha * f[j]);
-      }
-    }
-  }
 }
 
 // GemmParams here: m_blocks counts 256-row PAIR tiles, n_blocks counts 256-column tiles.
@@ -302,22 +208,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int n_blk = r - m_blk * p.n_blocks;
       const long long row = (long long)m_blk * (2 * kBM) + (long long)rank * kBM + q * 32 + lane;
       const bool row_ok = row < p.M;
+      float* sbias_tile = reinterpret_cast<float*>(smem + kBiasOffset2) + acc * 256;
+      epi_stage_bias(p, sbias_tile, n_blk * kBN2, kBN2);   // overlaps the MMAs of this tile
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_warp = tmem_base + acc * kBN2 + half * kColsPerWarp + (static_cast<uint32_t>(q * 32) << 16);
-      uint32_t vnext[32];
-      tmem_ld_32x32(t_warp, vnext);
-#pragma unroll 1
-      for (int c = 0; c < kColsPerWarp / 32; ++c) {
-        const int col0 = n_blk * kBN2 + half * kColsPerWarp + c * 32;
-        float f[32];
-        tmem_ld_wait_regs(vnext);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vnext[j]);
-        if (c + 1 < kColsPerWarp / 32) tmem_ld_32x32(t_warp + (c + 1) * 32, vnext);
-        if (col0 >= p.N) continue;
-        epi_apply_store<EPI>(p, f, row, row_ok, col0);
-      }
+      epi_run_store<EPI>(p, t_warp, row, row_ok, n_blk * kBN2, half * kColsPerWarp, kColsPerWarp, sbias_tile);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_addr(smem_u32(&tmem_empty[acc])));

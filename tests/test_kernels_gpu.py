@@ -24,6 +24,15 @@ def ops():
     return o
 
 
+@pytest.fixture(params=[1, 2], ids=["1cta", "2cta"])
+def gemm_mode(request):
+    """Force the 1-CTA kernel / the cta_group::2 pair kernel for every GEMM in the test."""
+    from clipa_b200 import _lib
+    _lib.check(_lib.lib().clipa_set_gemm_mode(request.param), "set_gemm_mode")
+    yield request.param
+    _lib.check(_lib.lib().clipa_set_gemm_mode(0), "set_gemm_mode")
+
+
 def relmax(got, ref):
     got, ref = got.float(), ref.float()
     assert torch.isfinite(got).all()
@@ -38,7 +47,7 @@ def mk(shape, dev, scale=1.0, seed=None):
                                    (333, 776, 200), (1000, 88, 72), (129, 264, 1032), (82 * 7, 768, 768),
                                    (4096, 3072, 1024)])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-def test_gemm_majors(dev, M, N, K, a_mn, b_mn):
+def test_gemm_majors(dev, gemm_mode, M, N, K, a_mn, b_mn):
     if (a_mn and M % 8) or (b_mn and N % 8) or (not a_mn and K % 8) or (not b_mn and K % 8):
         pytest.skip("row pitch of an operand would not be 16-byte aligned (rejected by the ABI; see test_gemm_rejects_bad_arguments)")
     torch.manual_seed(M * 7 + N * 3 + K)
@@ -49,7 +58,7 @@ def test_gemm_majors(dev, M, N, K, a_mn, b_mn):
     assert relmax(out, A.float() @ B.float().t()) < BF16_OUT
 
 
-def test_gemm_epilogues(dev):
+def test_gemm_epilogues(dev, gemm_mode):
     from clipa_b200._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_QUICK_GELU, EPI_ATOMIC_F32,
                                  EPI_BIAS_ACT, EPI_DACT)
     o = ops()
