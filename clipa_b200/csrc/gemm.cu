@@ -6,8 +6,8 @@
 namespace clipa {
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                       const CUtensorMap& tx, const GemmParams& p, int grid, cudaStream_t stream) {
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -17,15 +17,15 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                                           GemmSmem<BN>::kTotal));
     attr_set[dev] = true;
   }
-  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, stream>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, GemmSmem<BN>::kTotal, stream>>>(ta, tb, tc, tx, p);
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CLIPA_OK;
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
-                        cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                        const CUtensorMap& tx, const GemmParams& p, int grid, cudaStream_t stream) {
   auto kern = gemm_tc2_kernel<A_MN, B_MN, EPI>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -34,9 +34,27 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
     CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal2));
     attr_set[dev] = true;
   }
-  kern<<<grid, kGemmThreads, kSmemTotal2, stream>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, kSmemTotal2, stream>>>(ta, tb, tc, tx, p);
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
+  return CLIPA_OK;
+}
+
+// Output tensor maps for the TMA-store epilogue (bf16 C / aux, 32 x 32 boxes, 64-byte swizzle).
+// When the output is not bf16 (fp32 store / atomic accumulate) the maps are unused copies of `ta`.
+static int encode_out_maps(GemmParams& p, int epi, const CUtensorMap& ta, CUtensorMap* tc, CUtensorMap* tx) {
+  *tc = ta;
+  *tx = ta;
+  p.tma_store = 0;
+  const bool bf16_out = !p.c_f32 && (epi == EPI_STORE || epi == EPI_BIAS_ACT || epi == EPI_DACT);
+  if (!bf16_out) return CLIPA_OK;
+  int rc = encode_tmap_2d_bf16(tc, p.C, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc * 2, 32, 32, 64);
+  if (rc) return rc;
+  if (epi == EPI_BIAS_ACT && p.aux) {
+    rc = encode_tmap_2d_bf16(tx, p.aux, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldaux * 2, 32, 32, 64);
+    if (rc) return rc;
+  }
+  p.tma_store = 1;
   return CLIPA_OK;
 }
 
@@ -61,12 +79,15 @@ static int gemm_dispatch_2cta(GemmParams p, const void* A, long long lda, bool a
   if (!b_mn) rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldb * 2, kBK, kBN2 / 2);
   else       rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb * 2, 64, kBK);
   if (rc) return rc;
+  CUtensorMap tc, tx;
+  rc = encode_out_maps(p, epi, ta, &tc, &tx);
+  if (rc) return rc;
   int clusters = num_sms() / 2;
   if (max_ctas > 1 && max_ctas / 2 < clusters) clusters = max_ctas / 2;
   if (clusters > p.num_items) clusters = p.num_items;
   const int grid = clusters * 2;
 #define CLIPA_GEMM2_CASE(AMN_, BMN_, EPI_) \
-  if (a_mn == AMN_ && b_mn == BMN_ && epi == EPI_) return launch_gemm2<AMN_, BMN_, EPI_>(ta, tb, p, grid, stream);
+  if (a_mn == AMN_ && b_mn == BMN_ && epi == EPI_) return launch_gemm2<AMN_, BMN_, EPI_>(ta, tb, tc, tx, p, grid, stream);
   CLIPA_GEMM2_CASE(false, false, EPI_STORE)
   CLIPA_GEMM2_CASE(false, true, EPI_STORE)
   CLIPA_GEMM2_CASE(true, true, EPI_STORE)
@@ -116,13 +137,16 @@ int gemm_dispatch(GemmParams p, const void* A, long long lda, bool a_mn, const v
   else       rc = encode_tmap_2d_bf16(&tb, B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb * 2, 64, kBK);
   if (rc) return rc;
 
+  CUtensorMap tc, tx;
+  rc = encode_out_maps(p, epi, ta, &tc, &tx);
+  if (rc) return rc;
   int grid = num_sms();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (grid > p.num_items) grid = p.num_items;
 
 #define CLIPA_GEMM_CASE(BN_, AMN_, BMN_, EPI_)                                   \
   if (BN == BN_ && a_mn == AMN_ && b_mn == BMN_ && epi == EPI_)                  \
-    return launch_gemm<BN_, AMN_, BMN_, EPI_>(ta, tb, p, grid, stream);
+    return launch_gemm<BN_, AMN_, BMN_, EPI_>(ta, tb, tc, tx, p, grid, stream);
 #define CLIPA_GEMM_BOTH_BN(AMN_, BMN_, EPI_) \
   CLIPA_GEMM_CASE(256, AMN_, BMN_, EPI_) CLIPA_GEMM_CASE(128, AMN_, BMN_, EPI_)
 

@@ -45,6 +45,7 @@ struct GemmParams {
   __nv_bfloat16* aux;
   long long ldaux;
   int act;
+  int tma_store;  // bf16 outputs leave through per-warp smem staging + TMA store (tmap_c / tmap_aux)
   // contrastive head
   float scale_log2;  // logit_scale * log2(e)
   int label_offset;
@@ -63,7 +64,8 @@ struct GemmSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kBiasOffset = kBarOffset + 256;   // 2 x 256 fp32 bias slices (per accumulator stage)
-  static constexpr int kTotal = kBiasOffset + 2048 + 1024;  // + alignment slack
+  static constexpr int kStoreOffset = ((kBiasOffset + 2048 + 1023) / 1024) * 1024;  // 8 warps x 2 KB staging
+  static constexpr int kTotal = kStoreOffset + kNumEpiWarps * 2048 + 1024;  // + alignment slack
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -205,9 +207,38 @@ __device__ __forceinline__ const __nv_bfloat16* epi_side_ptr(const GemmParams& p
   ld = 0;
   return nullptr;
 }
+// One 32-row x 32-column bf16 chunk: registers -> 64B-swizzled per-warp staging buffer -> TMA store.
+// The TMA engine writes whole 64-byte row segments (and clips rows >= M / columns >= N), instead of
+// 32 lanes issuing 16-byte stores to 32 different cache lines through the LSU.
+__device__ __forceinline__ void chunk_store_tma(const CUtensorMap* tm, uint8_t* sbuf, const float (&f)[32],
+                                                int col0, int row0) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) tma_store_wait_read<0>();  // previous store has finished reading the staging buffer
+  __syncwarp();
+  uint8_t* rowp = sbuf + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint4 t;
+    t.x = pack_bf16x2(f[8 * k], f[8 * k + 1]);
+    t.y = pack_bf16x2(f[8 * k + 2], f[8 * k + 3]);
+    t.z = pack_bf16x2(f[8 * k + 4], f[8 * k + 5]);
+    t.w = pack_bf16x2(f[8 * k + 6], f[8 * k + 7]);
+    *reinterpret_cast<uint4*>(rowp + ((k ^ sw) << 4)) = t;
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tm, sbuf, col0, row0);
+    tma_store_commit();
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[32], long long row, bool row_ok,
-                                                int col0, const float* sb, const uint4 (&side)[4]) {
+                                                int col0, const float* sb, const uint4 (&side)[4],
+                                                const CUtensorMap* tm_c, const CUtensorMap* tm_aux, uint8_t* sbuf,
+                                                int row0_warp) {
   const bool full = (col0 + 32 <= p.N);
   if constexpr (EPI == EPI_STORE) {
 #pragma unroll
@@ -219,31 +250,37 @@ __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[
         f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
       }
     }
-    if (full) {
-      if (row_ok) {
-        if (p.residual) {
-          float rr[32];
-          unpack_bf16x32(side, rr);
+    if (p.residual && row_ok) {
+      if (full) {
+        float rr[32];
+        unpack_bf16x32(side, rr);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += rr[j];
-        }
+        for (int j = 0; j < 32; ++j) f[j] += rr[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) f[j] += __bfloat162float(p.residual[row * p.ldr + col0 + j]);
+      }
+    }
+    if (p.tma_store) {
+      chunk_store_tma(tm_c, sbuf, f, col0, row0_warp);
+    } else if (row_ok) {
+      if (full) {
         if (p.c_f32) store_f32x32(static_cast<float*>(p.C) + row * p.ldc + col0, f);
         else store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
-      }
-    } else if (row_ok) {
+      } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = col0 + j;
-        if (col < p.N) {
-          float x = f[j];
-          if (p.residual) x += __bfloat162float(p.residual[row * p.ldr + col]);
-          if (p.c_f32) static_cast<float*>(p.C)[row * p.ldc + col] = x;
-          else static_cast<__nv_bfloat16*>(p.C)[row * p.ldc + col] = __float2bfloat16(x);
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col < p.N) {
+            if (p.c_f32) static_cast<float*>(p.C)[row * p.ldc + col] = f[j];
+            else static_cast<__nv_bfloat16*>(p.C)[row * p.ldc + col] = __float2bfloat16(f[j]);
+          }
         }
       }
     }
   } else if constexpr (EPI == EPI_BIAS_ACT) {
-    // requires N % 32 == 0 (checked on the host)
+    // requires N % 32 == 0 (checked on the host); outputs always go through the TMA store
     if (p.bias) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -251,42 +288,38 @@ __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[
         f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
       }
     }
-    if (row_ok) {
-      if (p.aux) {
-        // the pre-activation is stored in bf16 and the activation is evaluated on the ROUNDED
-        // value, so backward (which re-reads aux) sees the same operand
-        store_bf16x32(p.aux + row * p.ldaux + col0, f);
+    if (p.aux) {
+      // the pre-activation is stored in bf16 and the activation is evaluated on the ROUNDED
+      // value, so backward (which re-reads aux) sees the same operand
+      chunk_store_tma(tm_aux, sbuf, f, col0, row0_warp);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
-      }
-      if (p.act == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 0);
-      } else if (p.act == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 1);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 2);
-      }
-      store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+      for (int j = 0; j < 32; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
     }
+    if (p.act == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 0);
+    } else if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 1);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 2);
+    }
+    chunk_store_tma(tm_c, sbuf, f, col0, row0_warp);
   } else if constexpr (EPI == EPI_DACT) {
-    if (row_ok) {
-      float a[32];
-      unpack_bf16x32(side, a);
-      if (p.act == 0) {
+    float a[32];
+    unpack_bf16x32(side, a);   // rows >= M carry zeros: their result is clipped by the TMA store
+    if (p.act == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 0);
-      } else if (p.act == 1) {
+      for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 0);
+    } else if (p.act == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 1);
-      } else {
+      for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 1);
+    } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 2);
-      }
-      store_bf16x32(static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0, f);
+      for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 2);
     }
+    chunk_store_tma(tm_c, sbuf, f, col0, row0_warp);
   } else if constexpr (EPI == EPI_ATOMIC_F32) {
     if (row_ok) {
       float* dst = static_cast<float*>(p.C) + row * p.ldc + col0;
@@ -307,7 +340,9 @@ __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[
 // tile-local column `col_local0`; TMEM loads and the side-operand loads run one chunk ahead.
 template <int EPI>
 __device__ __forceinline__ void epi_run_store(const GemmParams& p, uint32_t t_warp, long long row, bool row_ok,
-                                              int tile_col0, int col_local0, int ncols, const float* sbias_tile) {
+                                              int tile_col0, int col_local0, int ncols, const float* sbias_tile,
+                                              const CUtensorMap* tm_c, const CUtensorMap* tm_aux, uint8_t* sbuf) {
+  const int row0_warp = static_cast<int>(row) - static_cast<int>(threadIdx.x & 31);
   long long side_ld;
   const __nv_bfloat16* side_base = epi_side_ptr<EPI>(p, side_ld);
   const bool use_side = side_base != nullptr && row_ok;
@@ -339,10 +374,14 @@ __device__ __forceinline__ void epi_run_store(const GemmParams& p, uint32_t t_wa
         const uint4* q = reinterpret_cast<const uint4*>(side_base + row * side_ld + coln);
 #pragma unroll
         for (int i = 0; i < 4; ++i) side_next[i] = __ldg(q + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) side_next[i] = make_uint4(0, 0, 0, 0);
       }
     }
     if (col0 >= p.N) continue;  // warp-uniform
-    epi_apply_store<EPI>(p, f, row, row_ok, col0, sbias_tile + col_local0 + c * 32, side);
+    epi_apply_store<EPI>(p, f, row, row_ok, col0, sbias_tile + col_local0 + c * 32, side, tm_c, tm_aux, sbuf,
+                         row0_warp);
   }
 }
 
@@ -370,6 +409,7 @@ struct LseState {
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux,
                const GemmParams p) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
@@ -532,7 +572,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         const uint32_t t_warp = tmem_base + acc * BN + half * kColsPerWarp + (static_cast<uint32_t>(q * 32) << 16);
         if constexpr (EPI <= EPI_ATOMIC_F32) {
-          epi_run_store<EPI>(p, t_warp, row, row_ok, n_blk * BN, half * kColsPerWarp, kColsPerWarp, sbias_tile);
+          epi_run_store<EPI>(p, t_warp, row, row_ok, n_blk * BN, half * kColsPerWarp, kColsPerWarp, sbias_tile,
+                             &tmap_c, &tmap_aux, smem + S::kStoreOffset + ew * 2048);
         } else {
         uint32_t vnext[32];
         tmem_ld_32x32(t_warp, vnext);
@@ -614,6 +655,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 
   // teardown
+  if (warp >= 2 && lane == 0) tma_store_wait<0>();  // this warp's bulk stores have fully completed
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -23,7 +23,9 @@ constexpr int kBBytes2 = (kBN2 / 2) * kBK * 2; // this CTA's half of B
 constexpr int kStageBytes2 = kABytes2 + kBBytes2;
 constexpr int kBarOffset2 = kStages2 * kStageBytes2;
 constexpr int kBiasOffset2 = kBarOffset2 + 256;
-constexpr int kSmemTotal2 = kBiasOffset2 + 2048 + 1024;
+constexpr int kStoreOffset2 = ((kBiasOffset2 + 2048 + 1023) / 1024) * 1024;   // 8 warps x 2 KB staging
+constexpr int kSmemTotal2 = kStoreOffset2 + kNumEpiWarps * 2048 + 1024;
+static_assert(kSmemTotal2 <= 227 * 1024, "2-CTA GEMM shared memory budget");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -80,6 +82,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux,
                 const GemmParams p) {
   constexpr uint32_t kTmemCols = 2 * kBN2;
   constexpr uint32_t kIdesc = make_idesc_bf16(2 * kBM, kBN2, A_MN, B_MN);
@@ -213,7 +216,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_warp = tmem_base + acc * kBN2 + half * kColsPerWarp + (static_cast<uint32_t>(q * 32) << 16);
-      epi_run_store<EPI>(p, t_warp, row, row_ok, n_blk * kBN2, half * kColsPerWarp, kColsPerWarp, sbias_tile);
+      epi_run_store<EPI>(p, t_warp, row, row_ok, n_blk * kBN2, half * kColsPerWarp, kColsPerWarp, sbias_tile,
+                         &tmap_c, &tmap_aux, smem + kStoreOffset2 + ew * 2048);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_addr(smem_u32(&tmem_empty[acc])));
@@ -222,6 +226,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 
   // teardown: nobody may exit (or free TMEM) while the peer can still touch this CTA's smem/TMEM
+  if (warp >= 2 && lane == 0) tma_store_wait<0>();
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) {

@@ -51,7 +51,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,
-                        uint64_t pitch_bytes, uint32_t box0, uint32_t box1) {
+                        uint64_t pitch_bytes, uint32_t box0, uint32_t box1, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   CLIPA_REQUIRE(fn != nullptr, CLIPA_ERR_NO_DEVICE,
                 "cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");
@@ -65,7 +65,8 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint6
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CLIPA_REQUIRE(r == CUDA_SUCCESS, CLIPA_ERR_CUDA,
                 "cuTensorMapEncodeTiled failed (CUresult %d; dims %llu x %llu pitch %llu box %u x %u)",
