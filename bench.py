@@ -96,6 +96,24 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path (bounded sample of the same workload)
 # ------------------------------------------------------------------------------------------------
+def effective_cpus() -> int:
+    """Host cores this process may actually use: min(affinity mask, cgroup CPU quota).  os.cpu_count()
+    reports the machine's logical CPUs, which oversubscribes torch's thread pool inside a
+    quota-limited container (measured: 128 threads on a throttled box ran 100x slower)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_step_fn(wl, batch):
     import torch
     from clipa_b200.open_clip import get_model_config
@@ -117,11 +135,22 @@ def cpu_step_fn(wl, batch):
     return step
 
 
-def cpu_baseline(wl, budget_s=20.0, batch=8):
+def calibrated_cpu_step(wl, max_batch, target_s=5.0):
+    """Pick the sample size (pairs per CPU step) so that one oracle step takes ~target_s seconds."""
     import torch
-    cores = os.cpu_count() or 1
+    cores = effective_cpus()
     torch.set_num_threads(cores)
-    step = cpu_step_fn(wl, batch)
+    step1 = cpu_step_fn(wl, 1)
+    step1()                       # first call pays allocator / thread-pool start-up
+    t0 = time.perf_counter()
+    step1()
+    t1 = time.perf_counter() - t0
+    batch = int(max(1, min(max_batch, target_s / max(t1, 1e-3))))
+    return (step1 if batch == 1 else cpu_step_fn(wl, batch)), batch, cores
+
+
+def cpu_baseline(wl, budget_s=20.0, batch=8):
+    step, batch, cores = calibrated_cpu_step(wl, batch)
     step()  # warm-up
     t0 = time.perf_counter()
     n = 0
@@ -139,11 +168,7 @@ def run_reference_arm(args, wl, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    batch = args.cpu_batch
-    step = cpu_step_fn(wl, batch)
+    step, batch, cores = calibrated_cpu_step(wl, args.cpu_batch)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()

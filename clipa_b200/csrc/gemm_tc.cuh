@@ -85,35 +85,43 @@ __device__ __forceinline__ float fast_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// returns erf(|x|/sqrt2) in `erf_abs` and exp(-x^2/2) in `e`
-__device__ __forceinline__ void erf_half_core(float x, float& erf_abs, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  e = exp2f(-z * z * 1.4426950408889634f);
-  erf_abs = fmaf(-poly, e, 1.0f);
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// Upper-tail probability of the standard normal at |x| and the Gaussian factor, from the A-S 7.1.26
+// erfc form:  q = Phi(-|x|) = 0.5 * t*(a1 + t*(a2 + ...)) * exp(-x^2/2),  t = 1/(1 + p*|x|/sqrt2).
+// Everything is expressed in z' = |x| * sqrt(log2(e)/2) so that exp(-x^2/2) = 2^(-z'^2) is one
+// FMUL + one MUFU.EX2, and the 0.5 is folded into the coefficients.
+__device__ __forceinline__ void normal_tail(float x, float& q, float& e) {
+  const float zp = fabsf(x) * 0.84932180028801907f;             // |x| * sqrt(log2e / 2)
+  const float t = fast_rcp(fmaf(0.27273748087922250f, zp, 1.0f)); // p / sqrt(log2e)
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  e = fast_ex2(-zp * zp);
+  q = poly * t * e;
 }
 __device__ __forceinline__ float act_fwd(float x, int act) {
-  if (act == 0) {
-    float ea, e;
-    erf_half_core(x, ea, e);
-    return 0.5f * x * (1.0f + copysignf(ea, x));
+  if (act == 0) {  // x * Phi(x)
+    float q, e;
+    normal_tail(x, q, e);
+    const float r = x * q;
+    return x >= 0.f ? x - r : r;
   }
   if (act == 1) {
     const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
     return 0.5f * x * (1.0f + fast_tanh(u));
   }
-  return x * fast_rcp(1.0f + exp2f(-1.702f * 1.4426950408889634f * x));
+  return x * fast_rcp(1.0f + fast_ex2(-1.702f * 1.4426950408889634f * x));
 }
 __device__ __forceinline__ float act_bwd(float x, int act) {
-  if (act == 0) {
-    float ea, e;
-    erf_half_core(x, ea, e);
-    const float cdf = 0.5f * (1.0f + copysignf(ea, x));
+  if (act == 0) {  // Phi(x) + x * phi(x)
+    float q, e;
+    normal_tail(x, q, e);
+    const float cdf = x >= 0.f ? 1.0f - q : q;
     return fmaf(x * 0.3989422804014327f, e, cdf);
   }
   if (act == 1) {
@@ -123,7 +131,7 @@ __device__ __forceinline__ float act_bwd(float x, int act) {
     const float du = 0.7978845608028654f * fmaf(3.0f * 0.044715f, x2, 1.0f);
     return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
   }
-  const float sg = fast_rcp(1.0f + exp2f(-1.702f * 1.4426950408889634f * x));
+  const float sg = fast_rcp(1.0f + fast_ex2(-1.702f * 1.4426950408889634f * x));
   return sg * (1.0f + 1.702f * x * (1.0f - sg));
 }
 
