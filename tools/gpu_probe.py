@@ -249,6 +249,38 @@ def group_gemm_perf():
               f"{2.0 * M * N * K / ms2 / 1e9:.0f} TFLOP/s", flush=True)
 
 
+def group_gemm_epi_perf():
+    """Epilogue cost at the c_fc / c_proj-dgrad shapes (M = 82*1024 tokens)."""
+    M, D = 82 * 1024, 1024
+    x = mk((M, D)); w_fc = mk((4 * D, D), 0.03); b4 = torch.randn(4 * D, device=dev)
+    g = torch.empty(M, 4 * D, dtype=torch.bfloat16, device=dev)
+    f = torch.empty(M, 4 * D, dtype=torch.bfloat16, device=dev)
+    dy = mk((M, D)); w_pr = mk((D, 4 * D), 0.03); res = mk((M, D))
+    outD = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+    cases = {
+        "c_fc STORE(bias)": lambda: ops.gemm(x, w_fc, g, bias=b4),
+        "c_fc BIAS_ACT erf": lambda: ops.gemm(x, w_fc, g, epilogue=EPI_BIAS_ACT, bias=b4),
+        "c_fc BIAS_ACT erf +aux": lambda: ops.gemm(x, w_fc, g, epilogue=EPI_BIAS_ACT, bias=b4, aux=f),
+        "c_proj-dgrad STORE": lambda: ops.gemm(dy, w_pr.t(), g),
+        "c_proj-dgrad DACT erf": lambda: ops.gemm(dy, w_pr.t(), g, epilogue=EPI_DACT, aux=f),
+        "c_proj STORE(bias,res)": lambda: ops.gemm(g, w_pr, outD, bias=b4[:D].contiguous(), residual=res),
+        "out_proj STORE(bias,res)": lambda: ops.gemm(x, w_fc[:D], outD, bias=b4[:D].contiguous(), residual=res),
+        "out_proj STORE(bias)": lambda: ops.gemm(x, w_fc[:D], outD, bias=b4[:D].contiguous()),
+    }
+    flops = {"c_fc": 2.0 * M * 4 * D * D, "c_pr": 2.0 * M * 4 * D * D, "out_": 2.0 * M * D * D}
+    for name, fn in cases.items():
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"PERF {name:28s} {ms:.3f} ms  {flops[name[:4]] / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
     import os
     from clipa_b200 import _lib
