@@ -318,7 +318,7 @@ def main():
                        "micro_batch": min(bl, args.micro_batch),
                        "schedule": "plain fwd/bwd" if bl <= args.micro_batch else "GradCache (extra no-grad forward)",
                        "parallelism": f"dp{world}", "precision": args.precision,
-                       "optimizer": "AdamW (torch fused) inside the timed step", "l2": "inputs_exceed_L2",
+                       "optimizer": "AdamW (clipa_adamw_step: fused update + bf16 shadow + grad clear) inside the timed step", "l2": "inputs_exceed_L2",
                        "loss_last": float(last_loss),
                        "algorithmic_gflop_per_pair": wl["gflop_per_pair"],
                        "model_flops_utilization": per_gpu_pairs * wl["gflop_per_pair"] / (peak * 1e3)},

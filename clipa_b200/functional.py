@@ -26,8 +26,14 @@ def compute_copy(p: torch.Tensor) -> torch.Tensor:
     if p.dtype == _BF16:
         return p.detach()
     cache = getattr(p, "_clipa_bf16", None)
-    if cache is None or cache[0] != p._version:
+    if cache is None:
         cache = (p._version, p.detach().to(_BF16))
+        p._clipa_bf16 = cache
+    elif cache[0] != p._version:
+        # refresh IN PLACE: the shadow may be a view into the flat buffer that the fused optimizer
+        # kernel keeps up to date (clipa_b200.training.TrainStep)
+        cache[1].copy_(p.detach())
+        cache = (p._version, cache[1])
         p._clipa_bf16 = cache
     return cache[1]
 

@@ -10,9 +10,11 @@ accum_freq > 1 path (train.py:216-256) is used: features of all chunks are first
 autograd, the loss and d(features) are evaluated once on the whole (gathered) batch, then every
 chunk is re-run with autograd and back-propagated from its slice of d(features).
 
-Data parallelism: one process per GPU.  Parameters' gradients live in ONE flat fp32 buffer, so the
-data-parallel reduction is a single NCCL all-reduce (1.7 GB for ViT-L/14, ~4 ms on NVLink 5) issued
-after backward; at ~1 s per step it needs no bucketing or overlap.
+Data parallelism: one process per GPU.  Parameters' gradients live in flat fp32 buffers (one per
+weight-decay group), so the data-parallel reduction is two NCCL all-reduces (1.7 GB for ViT-L/14,
+~4 ms on NVLink 5) issued after backward; at ~0.8 s per step it needs no bucketing or overlap.  The
+optimizer is the fused clipa_adamw_step kernel over the same flat buffers (update + bf16 shadow
+weights + gradient clear + 1/world_size averaging in one pass).
 """
 from __future__ import annotations
 
@@ -35,7 +37,7 @@ class TrainStep:
                  lr: float = 1.024e-3, betas: Tuple[float, float] = (0.9, 0.95), eps: float = 1e-6,
                  wd: float = 0.2, micro_batch: int = 4096, local_loss: bool = True,
                  gather_with_grad: bool = True, image_mean=None, image_std=None,
-                 grad_clip_norm: Optional[float] = None):
+                 grad_clip_norm: Optional[float] = None, fused_optimizer: bool = True):
         self.model = model
         self.rank, self.world_size = rank, world_size
         self.micro_batch = micro_batch
@@ -50,21 +52,52 @@ class TrainStep:
         self._inv_std = (1.0 / torch.tensor(std, device=dev, dtype=torch.float32)).reshape(1, 3, 1, 1)
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         self.params = [p for _, p in named]
-        # flat gradient storage, grouped by dtype (fp32 masters; bf16 parameters in pure-bf16 mode)
-        self._flat = {}
-        for dt in {p.dtype for p in self.params}:
-            ps = [p for p in self.params if p.dtype == dt]
-            flat = torch.zeros(sum(p.numel() for p in ps), dtype=dt, device=dev)
-            off = 0
-            for p in ps:
-                p.grad = flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
-            self._flat[dt] = flat
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.step_count = 0
         gain = [p for n, p in named if exclude_from_wd(n, p)]
         rest = [p for n, p in named if not exclude_from_wd(n, p)]
-        self.optimizer = torch.optim.AdamW(
-            [{"params": gain, "weight_decay": 0.}, {"params": rest, "weight_decay": wd}],
-            lr=lr, betas=betas, eps=eps, fused=True)
+        self.fused = fused_optimizer and all(p.dtype == torch.float32 for p in self.params)
+        self._flat = {}
+        if self.fused:
+            # fp32 master weights: parameters, gradients, Adam moments and the bf16 shadow weights of
+            # each weight-decay group live in flat buffers (every tensor padded to 4 elements = 16 B),
+            # so one optimizer step is two launches of clipa_adamw_step and the data-parallel
+            # gradient reduction is one all-reduce per group.
+            self._groups = []
+            for ps, group_wd in ((gain, 0.0), (rest, wd)):
+                if not ps:
+                    continue
+                sizes = [(p.numel() + 3) // 4 * 4 for p in ps]
+                total = sum(sizes)
+                fp = torch.zeros(total, dtype=torch.float32, device=dev)
+                fg = torch.zeros(total, dtype=torch.float32, device=dev)
+                fb = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+                off = 0
+                for p, sz in zip(ps, sizes):
+                    n = p.numel()
+                    fp[off:off + n].copy_(p.data.reshape(-1))
+                    p.data = fp[off:off + n].view_as(p)
+                    p.grad = fg[off:off + n].view_as(p)
+                    shadow = fb[off:off + n].view_as(p)
+                    shadow.copy_(p.data)
+                    p._clipa_bf16 = (p._version, shadow)
+                    off += sz
+                self._groups.append(dict(p=fp, g=fg, m=torch.zeros_like(fp), v=torch.zeros_like(fp), b=fb, wd=group_wd))
+                self._flat[len(self._groups)] = fg
+            self.optimizer = None
+        else:
+            # pure-bf16 parameters (or fused_optimizer=False): flat gradient storage per dtype + torch AdamW
+            for dt in {p.dtype for p in self.params}:
+                ps = [p for p in self.params if p.dtype == dt]
+                flat = torch.zeros(sum(p.numel() for p in ps), dtype=dt, device=dev)
+                off = 0
+                for p in ps:
+                    p.grad = flat[off:off + p.numel()].view_as(p)
+                    off += p.numel()
+                self._flat[dt] = flat
+            self.optimizer = torch.optim.AdamW(
+                [{"params": gain, "weight_decay": 0.}, {"params": rest, "weight_decay": wd}],
+                lr=lr, betas=betas, eps=eps, fused=dev.type == "cuda")
 
     # -------------------------------------------------------------------------------------
     def preprocess(self, images: torch.Tensor) -> torch.Tensor:
@@ -78,11 +111,33 @@ class TrainStep:
         for flat in self._flat.values():
             flat.zero_()
 
-    def _allreduce_grads(self):
+    def _allreduce_grads(self, average: bool = True):
         if self.world_size > 1:
             for flat in self._flat.values():
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-                flat.div_(self.world_size)
+                if average:
+                    flat.div_(self.world_size)
+
+    def optimizer_step(self, grad_scale: float = 1.0):
+        """AdamW update; with the fused kernel the 1/world_size averaging, the bf16 shadow refresh and the
+        clearing of the gradient buffers ride along in the same pass."""
+        if not self.fused:
+            self.optimizer.step()
+            # torch's fused/foreach optimizers may update parameters without bumping their version
+            # counter, so the bf16 shadow weights are refreshed explicitly rather than lazily
+            with torch.no_grad():
+                for p in self.params:
+                    cache = getattr(p, "_clipa_bf16", None)
+                    if cache is not None:
+                        cache[1].copy_(p.detach())
+                        p._clipa_bf16 = (p._version, cache[1])
+            return
+        from . import ops
+        self.step_count += 1
+        for grp in self._groups:
+            ops.adamw_step(grp["p"], grp["g"], grp["m"], grp["v"], grp["b"], lr=self.lr, beta1=self.betas[0],
+                           beta2=self.betas[1], eps=self.eps, weight_decay=grp["wd"], step=self.step_count,
+                           grad_scale=grad_scale, zero_grad=True)
 
     def forward_backward(self, images: torch.Tensor, texts: torch.Tensor) -> torch.Tensor:
         model = self.model
@@ -121,12 +176,18 @@ class TrainStep:
         (device scalar, no host sync)."""
         images = self.preprocess(images)
         texts = texts.to(self.device, non_blocking=True)
-        self.zero_grad()
+        if not (self.fused and self.step_count > 0):
+            self.zero_grad()              # the fused optimizer kernel leaves the buffers cleared
         loss = self.forward_backward(images, texts)
-        self._allreduce_grads()
+        self._allreduce_grads(average=not self.fused)
+        scale = 1.0 / self.world_size if self.fused else 1.0
         if self.grad_clip_norm is not None:
-            torch.nn.utils.clip_grad_norm_(self.params, self.grad_clip_norm, norm_type=2.0)
-        self.optimizer.step()
+            if self.fused:   # ||scale * g|| over all groups; folded into the kernel's grad_scale
+                total = torch.sqrt(sum((f.float() ** 2).sum() for f in self._flat.values())).item() * scale
+                scale *= min(1.0, self.grad_clip_norm / (total + 1e-6))
+            else:
+                torch.nn.utils.clip_grad_norm_(self.params, self.grad_clip_norm, norm_type=2.0)
+        self.optimizer_step(grad_scale=scale)
         with torch.no_grad():
             self.model.logit_scale.clamp_(0, math.log(100))
         return loss

@@ -138,6 +138,18 @@ int clipa_clip_softmax_grad(const void* a, const void* b_all, int32_t b_local, i
                             int32_t E, float scale, int32_t label_offset, const float* lse,
                             void* pt, int64_t ldpt, float* dscale_partial, void* stream);
 
+/* ---- fused AdamW step ("next" row 8f.1) -----------------------------------------------------------
+ * torch.optim.AdamW as built at training/main.py:318-326 (decoupled weight decay, bias correction),
+ * over ONE flat fp32 segment of parameters that share a weight-decay value:
+ *   g' = grad_scale*g;  p *= 1 - lr*wd;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+ *   p -= (lr / (1-b1^step)) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
+ * In the same pass it refreshes the bf16 shadow copy the GEMMs read (param_bf16, may be NULL) and,
+ * if zero_grad != 0, clears the gradient segment for the next step.  n must be a multiple of 4 and
+ * every buffer 16-byte aligned; `step` counts from 1. */
+int clipa_adamw_step(void* param, void* grad, void* exp_avg, void* exp_avg_sq, void* param_bf16, int64_t n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                     float grad_scale, int32_t zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

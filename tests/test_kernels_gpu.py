@@ -223,3 +223,27 @@ def test_clip_loss_identical_pairs_full_size(dev):
     f = v.expand(8192, E).contiguous().requires_grad_(True)
     out = ClipLoss()(f, f, torch.tensor(14.285714, device=dev))
     assert abs(out.item() - math.log(8192)) < 1e-4
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.2])
+def test_fused_adamw_matches_torch(dev, wd):
+    """clipa_adamw_step == torch.optim.AdamW (training/main.py:318-326 recipe) over several steps,
+    incl. the bf16 shadow copy, the gradient clear and the folded gradient scale."""
+    o = ops()
+    torch.manual_seed(3)
+    n = 4096 * 33
+    p0 = torch.randn(n, device=dev)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1.024e-3, betas=(0.9, 0.95), eps=1e-6, weight_decay=wd)
+    p, m, v = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    for step in range(1, 6):
+        g = torch.randn(n, device=dev) * 0.1
+        ref.grad = (g * 0.5).clone()
+        opt.step()
+        gbuf = g.clone()
+        o.adamw_step(p, gbuf, m, v, shadow, lr=1.024e-3, beta1=0.9, beta2=0.95, eps=1e-6, weight_decay=wd,
+                     step=step, grad_scale=0.5, zero_grad=True)
+        assert torch.count_nonzero(gbuf).item() == 0
+    assert relmax(p, ref.detach()) < 1e-6
+    assert torch.equal(shadow, p.bfloat16())

@@ -173,3 +173,29 @@ def test_optimizer_step_reduces_loss(dev):
             model.logit_scale.clamp_(0, math.log(100))
         losses.append(loss.item())
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+def test_fused_train_step_matches_torch_optimizer_step(dev):
+    """TrainStep with the fused flat-buffer AdamW kernel == TrainStep with torch.optim.AdamW."""
+    from clipa_b200.training import TrainStep
+    from oracle.weights import make_inputs
+    meta, _ = load_golden("tiny-cls", "fp32")
+    images, text = make_inputs(meta["cfg"], 16, 5, image_size=meta["image_size"])
+    results = []
+    for fused in (True, False):
+        model = build_model(meta, "amp_bf16", dev)
+        ts = TrainStep(model, micro_batch=16, fused_optimizer=fused, lr=1e-3)
+        assert ts.fused == fused
+        losses = [ts.step(images, text).item() for _ in range(4)]
+        results.append((losses, {k: v.detach().float().clone() for k, v in model.state_dict().items()}))
+    (l_f, sd_f), (l_t, sd_t) = results
+    assert l_f[-1] < l_f[0], l_f
+    for a, b in zip(l_f, l_t):
+        assert abs(a - b) / abs(b) < 2e-2, (l_f, l_t)      # bf16 forward, atomics in wgrad: not bit-identical
+    # Adam's update is ~ +-lr per step whatever the gradient magnitude, so elements whose (noisy, bf16)
+    # gradient is near zero may legitimately differ by up to 2*lr*steps; nothing may differ by more.
+    bound = 2 * 1e-3 * 4 + 1e-4
+    worst = max(((sd_f[k] - sd_t[k]).abs().max().item(), k) for k in sd_f)
+    assert worst[0] <= bound, worst
+    moved = max((sd_f[k] - sd_t[k]).abs().mean().item() for k in sd_f)
+    assert moved < 1e-3, moved
