@@ -1,7 +1,7 @@
 cd /root/repo
 export PYTHONPATH=/root/repo
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 4 --warmup 3 > gpurun_out/bench_8gpu_gb32k.log 2> gpurun_out/bench_8gpu_gb32k.err
-tail -1 gpurun_out/bench_8gpu_gb32k.log | cut -c1-400; grep -v Warning gpurun_out/bench_8gpu_gb32k.err | tail -15 | cut -c1-300
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 4 --steps 3 --warmup 3 --no-e2e > gpurun_out/bench_4gpu_gb32k.log 2> gpurun_out/bench_4gpu_gb32k.err
-tail -1 gpurun_out/bench_4gpu_gb32k.log | cut -c1-400; grep -v Warning gpurun_out/bench_4gpu_gb32k.err | tail -5 | cut -c1-300
+ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches.csv python bench.py --global-batch 4096 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+tail -2 gpurun_out/bench_under_ncu.log | cut -c1-200
+python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launches_summary.txt; head -30 gpurun_out/launches_summary.txt
+gzip -f gpurun_out/launches.csv; ls -la gpurun_out/launches.csv.gz
