@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--save-ln", default="auto", choices=["auto", "on", "off"],
+                    help="keep LayerNorm outputs for backward (auto: when HBM allows)")
     ap.add_argument("--op-table", default=None, help="write the per-kernel CUDA-event table (JSON) to this path")
     args = ap.parse_args()
     name = args.workload
@@ -240,6 +242,8 @@ def main():
     if world > 1:  # identical replicas (DDP's initial broadcast, training/main.py:299)
         for p in model.parameters():
             dist.broadcast(p.data, 0)
+    from clipa_b200.open_clip.transformer import Transformer as _T
+    _T.save_ln_outputs = {"auto": "auto", "on": True, "off": False}[args.save_ln]
     model.train()
     trainer = TrainStep(model, rank=rank, world_size=world, micro_batch=args.micro_batch)
     ctx = model.context_length
@@ -320,6 +324,8 @@ def main():
                        "parallelism": f"dp{world}", "precision": args.precision,
                        "optimizer": "AdamW (clipa_adamw_step: fused update + bf16 shadow + grad clear) inside the timed step", "l2": "inputs_exceed_L2",
                        "loss_last": float(last_loss),
+                       "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
+                       "save_ln_outputs": str(type(model.visual.transformer).save_ln_outputs),
                        "algorithmic_gflop_per_pair": wl["gflop_per_pair"],
                        "model_flops_utilization": per_gpu_pairs * wl["gflop_per_pair"] / (peak * 1e3)},
             "clocks": clocks, "gpu_launches": launches,

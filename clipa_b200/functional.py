@@ -116,46 +116,50 @@ class ResidualBlockFn(torch.autograd.Function):
     """ResidualAttentionBlock.forward (open_clip/transformer.py:238-250) as one autograd node.
 
     Saved for backward: block input x, packed qkv, attention output, x1 (post-attention residual),
-    the attention log-sum-exp and the LayerNorm statistics -- 6 activation-sized tensors.  The two
-    LayerNorm outputs and the c_fc GEMM + activation are recomputed in backward (+11% FLOPs)
-    instead of keeping the 4x-wide MLP activations resident.
+    the attention log-sum-exp and the LayerNorm statistics -- 6 activation-sized tensors; with
+    `save_ln` also the two LayerNorm outputs (8 tensors; chosen by Transformer when HBM allows, it
+    removes two LayerNorm passes per block from backward).  The c_fc GEMM + activation is always
+    recomputed in backward (+11% FLOPs) instead of keeping the 4x-wide MLP activations resident.
     """
 
     @staticmethod
     def forward(ctx, x, ln1_w, ln1_b, w_in, b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj,
-                b_proj, batch, seq, heads, causal, act):
+                b_proj, batch, seq, heads, causal, act, save_ln):
         M, D = x.shape
         dev = x.device
         h1, mean1, rstd1 = ops.layernorm_fwd(x, _f32(ln1_w), _f32(ln1_b))
         qkv = torch.empty(M, 3 * D, dtype=_BF16, device=dev)
         ops.gemm(h1, compute_copy(w_in), qkv, bias=_bias(b_in))
-        del h1
+        if not save_ln:
+            h1 = None
         o, lse = ops.attention_fwd(qkv, batch, seq, heads, causal)
         x1 = torch.empty(M, D, dtype=_BF16, device=dev)
         ops.gemm(o, compute_copy(w_out), x1, bias=_bias(b_out), residual=x)
         h2, mean2, rstd2 = ops.layernorm_fwd(x1, _f32(ln2_w), _f32(ln2_b))
         g = torch.empty(M, w_fc.shape[0], dtype=_BF16, device=dev)
         ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), act=act)
-        del h2
+        if not save_ln:
+            h2 = None
         y = torch.empty(M, D, dtype=_BF16, device=dev)
         ops.gemm(g, compute_copy(w_proj), y, bias=_bias(b_proj), residual=x1)
         del g
         ctx.save_for_backward(x, qkv, o, lse, x1, mean1, rstd1, mean2, rstd2, ln1_w, ln1_b, w_in,
-                              b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj)
+                              b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj, h1, h2)
         ctx.meta = (batch, seq, heads, causal, act)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (x, qkv, o, lse, x1, mean1, rstd1, mean2, rstd2, ln1_w, ln1_b, w_in, b_in, w_out, b_out,
-         ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj) = ctx.saved_tensors
+         ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj, h1, h2) = ctx.saved_tensors
         batch, seq, heads, causal, act = ctx.meta
         M, D = x.shape
         dev = x.device
         dy = dy.contiguous()
         H4 = w_fc.shape[0]
-        # ---- MLP: recompute h2, f = c_fc(h2), g = act(f)
-        h2, _, _ = ops.layernorm_fwd(x1, _f32(ln2_w), _f32(ln2_b), save_stats=False)
+        # ---- MLP: (recompute h2,) f = c_fc(h2), g = act(f)
+        if h2 is None:
+            h2, _, _ = ops.layernorm_fwd(x1, _f32(ln2_w), _f32(ln2_b), save_stats=False)
         f = torch.empty(M, H4, dtype=_BF16, device=dev)
         g = torch.empty(M, H4, dtype=_BF16, device=dev)
         ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), aux=f, act=act)
@@ -182,7 +186,8 @@ class ResidualBlockFn(torch.autograd.Function):
         ops.gemm(dx1, compute_copy(w_out).t(), do)
         dqkv = ops.attention_bwd(qkv, o, do, lse, batch, seq, heads, causal)
         del do
-        h1, _, _ = ops.layernorm_fwd(x, _f32(ln1_w), _f32(ln1_b), save_stats=False)
+        if h1 is None:
+            h1, _, _ = ops.layernorm_fwd(x, _f32(ln1_w), _f32(ln1_b), save_stats=False)
         d_w_in = _wgrad(dqkv, h1, w_in)
         d_b_in = _bgrad(dqkv, b_in)
         del h1
@@ -194,7 +199,7 @@ class ResidualBlockFn(torch.autograd.Function):
         dx = ops.layernorm_bwd(dh1, x, _f32(ln1_w), mean1, rstd1, dx1, d_ln1_w, d_ln1_b)
         return (dx, d_ln1_w.to(ln1_w.dtype), d_ln1_b.to(ln1_b.dtype), d_w_in, d_b_in, d_w_out, d_b_out,
                 d_ln2_w.to(ln2_w.dtype), d_ln2_b.to(ln2_b.dtype), d_w_fc, d_b_fc, d_w_proj, d_b_proj,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 class ClipLossFn(torch.autograd.Function):

@@ -58,13 +58,13 @@ class ResidualAttentionBlock(nn.Module):
         self.n_head = n_head
         self.act = ACT_BY_NAME[act]
 
-    def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool):
+    def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool, save_ln: bool = False):
         """x: [batch*seq, d_model] bf16, sample-major rows."""
         return Fn.ResidualBlockFn.apply(
             x, self.ln_1.weight, self.ln_1.bias, self.attn.in_proj_weight, self.attn.in_proj_bias,
             self.attn.out_proj.weight, self.attn.out_proj.bias, self.ln_2.weight, self.ln_2.bias,
             self.mlp.c_fc.weight, self.mlp.c_fc.bias, self.mlp.c_proj.weight, self.mlp.c_proj.bias,
-            batch, seq, self.n_head, causal, self.act)
+            batch, seq, self.n_head, causal, self.act, save_ln)
 
 
 class Transformer(nn.Module):
@@ -84,9 +84,25 @@ class Transformer(nn.Module):
     def get_cast_dtype(self) -> torch.dtype:
         return self.resblocks[0].mlp.c_fc.weight.dtype
 
+    # 'auto': keep the LayerNorm outputs of every block for backward when they fit comfortably in
+    # free HBM (2 extra activation-sized tensors per block), else recompute them; True / False force it.
+    save_ln_outputs = "auto"
+
+    def _decide_save_ln(self, x: torch.Tensor) -> bool:
+        if not torch.is_grad_enabled() or not x.is_cuda:
+            return False
+        if self.save_ln_outputs != "auto":
+            return bool(self.save_ln_outputs)
+        unit = x.numel() * x.element_size()
+        need = (8 * self.layers + 16) * unit          # 8 saved tensors per block + backward temporaries
+        free, _ = torch.cuda.mem_get_info(x.device)
+        free += torch.cuda.memory_reserved(x.device) - torch.cuda.memory_allocated(x.device)
+        return need + (16 << 30) < free                # keep a 16 GB margin for the other tower / head
+
     def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool = False):
+        save_ln = self._decide_save_ln(x)
         for r in self.resblocks:
-            x = r(x, batch, seq, causal)
+            x = r(x, batch, seq, causal, save_ln)
         return x
 
 

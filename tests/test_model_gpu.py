@@ -199,3 +199,22 @@ def test_fused_train_step_matches_torch_optimizer_step(dev):
     assert worst[0] <= bound, worst
     moved = max((sd_f[k] - sd_t[k]).abs().mean().item() for k in sd_f)
     assert moved < 1e-3, moved
+
+
+def test_activation_policy_save_ln_equals_recompute(dev):
+    """Keeping the LayerNorm outputs for backward (save_ln_outputs) and recomputing them are the same math."""
+    from clipa_b200.open_clip.transformer import Transformer
+    meta, _ = load_golden("tiny-gap-h80", "fp32")
+    grads = []
+    old = Transformer.save_ln_outputs
+    try:
+        for policy in (True, False):
+            Transformer.save_ln_outputs = policy
+            model, _, _, loss = run_ours(meta, "amp_bf16", dev)
+            grads.append((loss.item(), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}))
+    finally:
+        Transformer.save_ln_outputs = old
+    (l0, g0), (l1, g1) = grads
+    assert l0 == l1
+    for n in g0:
+        assert rel_err(g0[n].cpu(), g1[n].cpu()) < 1e-3, n     # only fp32-atomic summation order differs

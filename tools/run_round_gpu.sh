@@ -1,7 +1,8 @@
 cd /root/repo
 export PYTHONPATH=/root/repo
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches.csv python bench.py --global-batch 4096 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-tail -2 gpurun_out/bench_under_ncu.log | cut -c1-200
-python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launches_summary.txt; head -30 gpurun_out/launches_summary.txt
-gzip -f gpurun_out/launches.csv; ls -la gpurun_out/launches.csv.gz
+timeout 600 python -m pytest tests/test_model_gpu.py -m gpu -x -q 2>&1 | tail -3
+for pol in off on off on; do
+python bench.py --global-batch 4096 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --save-ln $pol 2>/dev/null | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('save_ln', '$pol', 'ms', round(d['ms_per_step'],1), 'pairs/s', round(d['value'],1), 'peak_hbm_gb', d['config']['peak_hbm_gb'], d['clocks']['sm_mhz'])"
+done
