@@ -12,6 +12,13 @@
 //                                                            later tcgen05.ld O row -> 1/l -> 128 B store
 // The score matrix lives only in TMEM/registers; per problem HBM traffic is the algorithmic
 // minimum (Q, K, V read once, O written once).
+//
+// Short sequences are PACKED: G = floor(128 / L) consecutive samples of the same head share one
+// M = 128 tile (text towers: 8 x 16 tokens, 16 x 8 tokens); the score tile is then block-diagonal --
+// row i only attends to the columns of its own sample -- and every warp touches only the 32-column
+// chunks its rows' blocks overlap, so the work per sample does not grow with the packing.
+#include <type_traits>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -29,9 +36,35 @@ struct AttnTcParams {
   __nv_bfloat16* out;
   float* lse;
   int L, H, batch;
-  int npad;  // ceil16(L)
+  int G;     // samples packed per 128-row tile
+  int GL;    // G * L rows / keys in use per tile
+  int npad;  // ceil16(G * L)
   float scale_log2;
 };
+
+// Per-thread view of the packing: which key columns row `row` may attend to.
+struct RowSpan {
+  int lo, hi;     // valid key columns [lo, hi)
+  int sample;     // sample index within the tile
+  int token;      // token index within the sample
+};
+template <bool CAUSAL, bool PACKED>
+__device__ __forceinline__ RowSpan row_span(int row, int L, int GL) {
+  RowSpan r;
+  if (!PACKED) {   // one sample per tile: everything folds to the unpacked constants
+    r.sample = 0;
+    r.lo = 0;
+    r.token = row;
+    r.hi = CAUSAL ? row + 1 : L;
+    return r;
+  }
+  const int rr = min(row, GL - 1);
+  r.sample = rr / L;
+  r.lo = r.sample * L;
+  r.token = rr - r.lo;
+  r.hi = CAUSAL ? rr + 1 : r.lo + L;
+  return r;
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float r;
@@ -52,7 +85,8 @@ __device__ __forceinline__ uint32_t p_tile_off(int row, int chunk) {
   return (chunk >> 3) * kTcTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
 }
 
-template <int NCH, bool CAUSAL>  // NCH = 32-column chunks of the score row held in registers
+// NCH = 32-column chunks of the score row held in registers; PACKED = more than one sample per tile
+template <int NCH, bool CAUSAL, bool PACKED>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -70,7 +104,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L, H = p.H, D = H * kTcHd;
-  const int total = p.batch * H;
+  const int tiles_per_head = (p.batch + p.G - 1) / p.G;
+  const int total = tiles_per_head * H;
 
   // Stale rows [L,128) of the K/V tiles are multiplied by exactly-zero probabilities, so they must
   // never hold NaN/Inf bit patterns: zero everything once.
@@ -104,10 +139,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
         const int prob = blockIdx.x + i * gridDim.x;
-        const int n = prob / H, h = prob - n * H;
+        const int n = (prob / H) * p.G, h = prob % H;   // first sample of the tile, head
         mbar_wait(&kv_empty[s], ph ^ 1);
         uint8_t* st = smem + s * kTcStageBytes;
-        mbar_expect_tx(&full[s], 3u * (uint32_t)L * 128u);
+        mbar_expect_tx(&full[s], 3u * (uint32_t)p.GL * 128u);
         tma_load_2d(st, &tmap_qkv, &full[s], h * kTcHd, n * L);
         tma_load_2d(st + kTcTileBytes, &tmap_qkv, &full[s], D + h * kTcHd, n * L);
         tma_load_2d(st + 2 * kTcTileBytes, &tmap_qkv, &full[s], 2 * D + h * kTcHd, n * L);
@@ -158,14 +193,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
     const int grp = (warp - 2) >> 2;  // 0: even problems, 1: odd problems
     const int q = warp & 3;           // TMEM lane quarter
     const int row = q * 32 + lane;    // query index handled by this thread
-    const bool warp_has_rows = q * 32 < L;  // warp-uniform: all 32 rows beyond L -> nothing to compute
+    const bool warp_has_rows = q * 32 < p.GL;  // warp-uniform: all 32 rows beyond the tile's rows -> idle
+    const RowSpan span = row_span<CAUSAL, PACKED>(row, L, p.GL);
+    // 32-column chunks this WARP has to look at: from its first row's block to its last row's block
+    const int c_first = PACKED ? (min(q * 32, p.GL - 1) / L * L) >> 5 : 0;
+    const int c_last = PACKED ? (min(p.GL, (min(q * 32 + 31, p.GL - 1) / L + 1) * L) - 1) >> 5 : NCH - 1;
     uint8_t* pbuf = p_base + grp * kTcPBytes;
     const uint32_t t_s = tmem_base + grp * 256 + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t t_o = t_s + 128;
     for (int i = grp; i < n_local; i += 2) {
       const uint32_t ph = (i >> 1) & 1;
       const int prob = blockIdx.x + i * gridDim.x;
-      const int n = prob / H, h = prob - n * H;
+      const int n = (prob / H) * p.G, h = prob % H;
+      const bool row_valid = row < p.GL && n + span.sample < p.batch;
       mbar_wait(&s_full[grp], ph);
       tc_fence_after();
       float l = 0.f, ms = 0.f;
@@ -174,18 +214,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         // (TMEM reads are the scarce resource: ~64 B/clk/SM), then max -> exp2 -> sum -> bf16 P.
         uint32_t v[NCH][32];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, v[c]);
+        for (int c = 0; c < NCH; ++c)
+          if (c >= c_first && c <= c_last) tmem_ld_32x32(t_s + c * 32, v[c]);
         tmem_ld_wait();
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
+          if (c >= c_first && c <= c_last) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int key = c * 32 + j;
-            float x = __uint_as_float(v[c][j]);
-            if (key >= L || (CAUSAL && key > row)) x = -INFINITY;
-            v[c][j] = __float_as_uint(x);
-            mx[j & 3] = fmaxf(mx[j & 3], x);
+            for (int j = 0; j < 32; ++j) {
+              const int key = c * 32 + j;
+              float x = __uint_as_float(v[c][j]);
+              if ((PACKED && key < span.lo) || key >= span.hi) x = -INFINITY;
+              v[c][j] = __float_as_uint(x);
+              mx[j & 3] = fmaxf(mx[j & 3], x);
+            }
           }
         }
         const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
@@ -193,15 +236,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         float sm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          float pr[32];
+          if (c >= c_first && c <= c_last) {   // chunks outside the warp's blocks stay zero in smem forever
+            float pr[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            pr[j] = ex2_approx(fmaf(__uint_as_float(v[c][j]), p.scale_log2, -ms));  // exp2(-inf) = 0
-            sm[j & 3] += pr[j];
+            for (int j = 0; j < 32; ++j) {
+              pr[j] = ex2_approx(fmaf(__uint_as_float(v[c][j]), p.scale_log2, -ms));  // exp2(-inf) = 0
+              sm[j & 3] += pr[j];
+            }
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8)
+              *reinterpret_cast<uint4*>(pbuf + p_tile_off(row, c * 4 + g8)) = pack8_bf16(pr + 8 * g8);
           }
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8)
-            *reinterpret_cast<uint4*>(pbuf + p_tile_off(row, c * 4 + g8)) = pack8_bf16(pr + 8 * g8);
         }
         l = (sm[0] + sm[1]) + (sm[2] + sm[3]);
         fence_proxy_async_smem();  // generic-proxy P stores -> visible to the MMA (async proxy)
@@ -221,7 +266,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_free[grp]);
-        if (row < L) {
+        if (row_valid) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)n * L + row) * D + h * kTcHd);
           float f[32];
 #pragma unroll
@@ -232,7 +277,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(o1[j]) * inv;
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) dst[4 + g8] = pack8_bf16(f + 8 * g8);
-          p.lse[((long long)n * H + h) * L + row] = (ms + log2f(l)) * 0.69314718055994531f;
+          p.lse[((long long)(n + span.sample) * H + h) * L + span.token] = (ms + log2f(l)) * 0.69314718055994531f;
         }
       } else {
         tc_fence_before();
@@ -257,16 +302,19 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, i
   const int D = H * kTcHd;
   CUtensorMap tm;
   // 2-D view of the packed qkv matrix: inner = 3D columns, outer = batch*L rows; box = 64 cols x L rows
+  const int G = 128 / L;   // samples per tile
+  const int GL = G * L;
   int rc = encode_tmap_2d_bf16(&tm, qkv, (uint64_t)3 * D, (uint64_t)batch * L, (uint64_t)3 * D * 2, kTcHd,
-                               (uint32_t)L);
+                               (uint32_t)GL);
   if (rc) return rc;
   AttnTcParams p;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
   p.L = L; p.H = H; p.batch = batch;
-  p.npad = (L + 15) & ~15;
+  p.G = G; p.GL = GL;
+  p.npad = (GL + 15) & ~15;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)kTcHd);
-  long long total = (long long)batch * H;
+  long long total = (long long)((batch + G - 1) / G) * H;
   int grid = num_sms();
   if (grid > total) grid = (int)total;
   const int nch = (p.npad + 31) / 32;
@@ -275,22 +323,18 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, i
     kern<<<grid, kTcThreads, kTcSmemTotal, stream>>>(tm, p);
     return CLIPA_OK;
   };
-  int lrc;
-  if (causal) {
+  auto pick = [&](auto causal_c, auto packed_c) -> int {
+    constexpr bool C = decltype(causal_c)::value, P = decltype(packed_c)::value;
     switch (nch) {
-      case 1: lrc = launch(attn_fwd_tc_kernel<1, true>); break;
-      case 2: lrc = launch(attn_fwd_tc_kernel<2, true>); break;
-      case 3: lrc = launch(attn_fwd_tc_kernel<3, true>); break;
-      default: lrc = launch(attn_fwd_tc_kernel<4, true>); break;
+      case 1: return launch(attn_fwd_tc_kernel<1, C, P>);
+      case 2: return launch(attn_fwd_tc_kernel<2, C, P>);
+      case 3: return launch(attn_fwd_tc_kernel<3, C, P>);
+      default: return launch(attn_fwd_tc_kernel<4, C, P>);
     }
-  } else {
-    switch (nch) {
-      case 1: lrc = launch(attn_fwd_tc_kernel<1, false>); break;
-      case 2: lrc = launch(attn_fwd_tc_kernel<2, false>); break;
-      case 3: lrc = launch(attn_fwd_tc_kernel<3, false>); break;
-      default: lrc = launch(attn_fwd_tc_kernel<4, false>); break;
-    }
-  }
+  };
+  using T = std::true_type;
+  using F = std::false_type;
+  const int lrc = causal ? (G > 1 ? pick(T{}, T{}) : pick(T{}, F{})) : (G > 1 ? pick(F{}, T{}) : pick(F{}, F{}));
   if (lrc) return lrc;
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -323,6 +367,7 @@ struct AttnBwParams {
   const float* lse;
   __nv_bfloat16* dqkv;
   int L, H, batch;
+  int G, GL;   // samples per tile, rows in use (see AttnTcParams)
   int npad;
   float scale;
 };
@@ -342,7 +387,7 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, uint32_t ta
   }
 }
 
-template <bool CAUSAL>
+template <bool CAUSAL, bool PACKED>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                    const __grid_constant__ CUtensorMap tmap_o, const AttnBwParams p) {
@@ -362,7 +407,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L, H = p.H, D = H * kTcHd;
-  const int total = p.batch * H;
+  const int tiles_per_head = (p.batch + p.G - 1) / p.G;
+  const int total = tiles_per_head * H;
   const long long pitch = 3LL * D;
 
   for (int i = threadIdx.x; i < kBwSmemBar / 16; i += blockDim.x)
@@ -397,10 +443,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
         const int prob = blockIdx.x + i * gridDim.x;
-        const int n = prob / H, h = prob - n * H;
+        const int n = (prob / H) * p.G, h = prob % H;
         mbar_wait(&kv_empty[s], ph ^ 1);
         uint8_t* st = smem + s * kBwStageBytes;
-        mbar_expect_tx(&full[s], (uint32_t)kBwTiles * (uint32_t)L * 128u);
+        mbar_expect_tx(&full[s], (uint32_t)kBwTiles * (uint32_t)p.GL * 128u);
         tma_load_2d(st, &tmap_qkv, &full[s], h * kTcHd, n * L);
         tma_load_2d(st + kTcTileBytes, &tmap_qkv, &full[s], D + h * kTcHd, n * L);
         tma_load_2d(st + 2 * kTcTileBytes, &tmap_qkv, &full[s], 2 * D + h * kTcHd, n * L);
@@ -459,27 +505,38 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;     // which half of the columns
     const int row = q * 32 + lane;        // query index (elementwise stage) / key index (dK, dV rows)
-    const bool row_ok = row < L;
+    const bool row_in_tile = row < p.GL;
+    const RowSpan span = row_span<CAUSAL, PACKED>(row, L, p.GL);
     const bool warp_writes = q * 32 < p.npad;  // rows >= npad are never contracted: skip their P/dS
-    const bool warp_stores = q * 32 < L;       // rows >= L have no gradient rows to store
+    const bool warp_stores = q * 32 < p.GL;    // rows beyond the tile's rows have no gradient rows to store
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float scale_log2 = p.scale * 1.4426950408889634f;
-    const int c_begin = half * 64;
-    const int c_end = min(p.npad, c_begin + 64);
+    // 32-column chunks of this warp's column half that its rows' blocks overlap (block-diagonal tile)
+    const int blk_lo = PACKED ? min(q * 32, p.GL - 1) / L * L : 0;
+    const int blk_hi = PACKED ? min(p.GL, (min(q * 32 + 31, p.GL - 1) / L + 1) * L) : L;
+    const int c_begin = max(half * 64, blk_lo & ~31);
+    const int c_end = min(min(p.npad, half * 64 + 64), (blk_hi + 31) & ~31);
+    auto lse_index = [&](int prob) -> long long {   // lse is [batch, H, L]
+      const int n = (prob / H) * p.G + span.sample, h = prob % H;
+      return n < p.batch ? ((long long)n * H + h) * L + span.token : -1;
+    };
     float lse2_next = 0.f;
-    if (n_local > 0 && row_ok) {
-      const int prob0 = blockIdx.x;
-      lse2_next = p.lse[(long long)prob0 * L + row] * 1.4426950408889634f;   // lse is [batch, H, L]
+    if (n_local > 0 && row_in_tile) {
+      const long long li = lse_index(blockIdx.x);
+      if (li >= 0) lse2_next = p.lse[li] * 1.4426950408889634f;
     }
     for (int i = 0; i < n_local; ++i) {
       const int s = i & 1;
       const uint32_t ph = (i >> 1) & 1;
       const uint32_t pi = i & 1;
       const int prob = blockIdx.x + i * gridDim.x;
-      const int n = prob / H, h = prob - n * H;
+      const int n = (prob / H) * p.G, h = prob % H;
+      const bool row_ok = row_in_tile && n + span.sample < p.batch;
       const float lse2 = lse2_next;
-      if (i + 1 < n_local && row_ok)  // prefetch the next problem's lse (one float per thread)
-        lse2_next = p.lse[(long long)(prob + (int)gridDim.x) * L + row] * 1.4426950408889634f;
+      if (i + 1 < n_local && row_in_tile) {  // prefetch the next problem's lse (one float per thread)
+        const long long li = lse_index(prob + (int)gridDim.x);
+        lse2_next = li >= 0 ? p.lse[li] * 1.4426950408889634f : 0.f;
+      }
       // delta_i = sum_d dO_id * O_id from the swizzled smem tiles (TMA already landed them)
       mbar_wait(&full[s], ph);
       float delta = 0.f;
@@ -511,7 +568,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int key = c + j;
-            const bool ok = row_ok && (key < L) && !(CAUSAL && key > row);
+            const bool ok = row_ok && (!PACKED || key >= span.lo) && key < span.hi;
             const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[j]), scale_log2, -lse2)) : 0.f;
             pr[j] = pv;
             ds[j] = pv * (__uint_as_float(dv[j]) - delta) * p.scale;
@@ -557,20 +614,22 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const f
   CLIPA_REQUIRE(L >= 1 && L <= 128, CLIPA_ERR_UNSUPPORTED, "attention_bwd_tc: L=%d > 128", L);
   const int D = H * kTcHd;
   CUtensorMap tq, td, to;
+  const int G = 128 / L, GL = G * L;
   int rc = encode_tmap_2d_bf16(&tq, qkv, (uint64_t)3 * D, (uint64_t)batch * L, (uint64_t)3 * D * 2, kTcHd,
-                               (uint32_t)L);
+                               (uint32_t)GL);
   if (rc) return rc;
-  rc = encode_tmap_2d_bf16(&td, dout, (uint64_t)D, (uint64_t)batch * L, (uint64_t)D * 2, kTcHd, (uint32_t)L);
+  rc = encode_tmap_2d_bf16(&td, dout, (uint64_t)D, (uint64_t)batch * L, (uint64_t)D * 2, kTcHd, (uint32_t)GL);
   if (rc) return rc;
-  rc = encode_tmap_2d_bf16(&to, out, (uint64_t)D, (uint64_t)batch * L, (uint64_t)D * 2, kTcHd, (uint32_t)L);
+  rc = encode_tmap_2d_bf16(&to, out, (uint64_t)D, (uint64_t)batch * L, (uint64_t)D * 2, kTcHd, (uint32_t)GL);
   if (rc) return rc;
   AttnBwParams p;
   p.lse = lse;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   p.L = L; p.H = H; p.batch = batch;
-  p.npad = (L + 15) & ~15;
+  p.G = G; p.GL = GL;
+  p.npad = (GL + 15) & ~15;
   p.scale = 1.0f / sqrtf((float)kTcHd);
-  long long total = (long long)batch * H;
+  long long total = (long long)((batch + G - 1) / G) * H;
   int grid = num_sms();
   if (grid > total) grid = (int)total;
   auto launch = [&](auto kern) -> int {
@@ -578,7 +637,8 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const f
     kern<<<grid, kTcThreads, kBwSmemTotal, stream>>>(tq, td, to, p);
     return CLIPA_OK;
   };
-  const int lrc = causal ? launch(attn_bwd_tc_kernel<true>) : launch(attn_bwd_tc_kernel<false>);
+  const int lrc = causal ? (G > 1 ? launch(attn_bwd_tc_kernel<true, true>) : launch(attn_bwd_tc_kernel<true, false>))
+                         : (G > 1 ? launch(attn_bwd_tc_kernel<false, true>) : launch(attn_bwd_tc_kernel<false, false>));
   if (lrc) return lrc;
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -151,7 +151,12 @@ def test_colsum(dev):
 
 @pytest.mark.parametrize("B,L,H,hd,causal", [(3, 82, 16, 64, False), (5, 16, 12, 64, True), (2, 37, 16, 80, False),
                                              (2, 257, 4, 64, False), (4, 8, 16, 64, True), (2, 65, 12, 64, False),
-                                             (3, 32, 12, 64, True), (2, 100, 2, 64, True), (1, 1, 2, 64, True)])
+                                             (3, 32, 12, 64, True), (2, 100, 2, 64, True), (1, 1, 2, 64, True),
+                                             # packed tiles (several samples per 128-row tile): partial last
+                                             # tile, blocks straddling 32-column chunks, G*L < 128, one sample
+                                             (19, 16, 12, 64, True), (21, 16, 4, 64, False), (9, 8, 16, 64, True),
+                                             (7, 33, 4, 64, True), (5, 48, 2, 64, False), (11, 63, 2, 64, True),
+                                             (300, 16, 12, 64, True), (3, 64, 2, 64, False), (1, 5, 2, 64, True)])
 def test_attention(dev, B, L, H, hd, causal):
     o = ops()
     torch.manual_seed(B * 100 + L)

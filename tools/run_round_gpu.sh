@@ -1,13 +1,20 @@
-cd /root/repo
-export PYTHONPATH=/root/repo
-mkdir -p gpurun_out
-for w in "vitb16_i64_t16_gb16k 2048" "vitl14_i256_t32_gb16k 2048" "vith14_i36_t8_gb64k 8192"; do
-set -- $w
-python bench.py --workload $1 --global-batch $2 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --op-table gpurun_out/op_table_$1.json > gpurun_out/bench_$1.log 2> gpurun_out/bench_$1.err
-tail -1 gpurun_out/bench_$1.log | python -c "
+#!/bin/bash
+# scratch driver for one gpurun call
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out/pack
+export PYTHONPATH="$PWD:$PYTHONPATH"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/pack/gpu.txt 2>&1
+timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "attention" > gpurun_out/pack/pytest_attn.log 2>&1
+echo "pytest attn exit=$?"; tail -n 5 gpurun_out/pack/pytest_attn.log
+echo "--- new"; timeout 300 python tools/prof_attn_text.py 2>&1 | tee gpurun_out/pack/perf_new.log
+echo "--- old"; CLIPA_B200_LIB=$PWD/clipa_b200/lib/libclipa_b200_oldattn.so timeout 300 python tools/prof_attn_text.py 2>&1 | tee gpurun_out/pack/perf_old.log
+for v in new old; do
+  if [ $v = old ]; then export CLIPA_B200_LIB=$PWD/clipa_b200/lib/libclipa_b200_oldattn.so; else unset CLIPA_B200_LIB; fi
+  timeout 600 python bench.py --global-batch 4096 --micro-batch 4096 --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/pack/bench_$v.json 2> gpurun_out/pack/bench_$v.err
+  echo "bench $v exit=$?"; python -c "
 import json,sys
-try:
-    d=json.loads(sys.stdin.read()); print('$1', 'B', d['config']['global_batch'], 'ms', round(d['ms_per_step'],1), 'pairs/s', round(d['value'],1), 'mfu', round(d['config']['model_flops_utilization'],3), 'gemm TF', round(d['roofline']['achieved'],1), 'peak GB', d['config']['peak_hbm_gb'], 'loss', round(d['config']['loss_last'],3))
-except Exception as e: print('$1 FAILED', e)"
-grep -v Warn gpurun_out/bench_$1.err | tail -3 | cut -c1-300
+d=json.loads(open('gpurun_out/pack/bench_$v.json').read().strip().splitlines()[-1]); print('$v', d['value'], d['ms_per_step'], d['clocks'])"
 done
+unset CLIPA_B200_LIB
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pack/pytest_all.log 2>&1
+echo "pytest all exit=$?"; tail -n 5 gpurun_out/pack/pytest_all.log
