@@ -460,12 +460,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const uint32_t idesc_t = make_idesc_bf16(128, kTcHd, true, true);                // A MN (P^T/dS^T), B MN
       const uint32_t idesc_q = make_idesc_bf16(128, kTcHd, false, true);               // A K (dS), B MN (K)
       const int ksteps = p.npad / 16;
-      for (int i = 0; i < n_local; ++i) {
+      // S and dP of problem i+1 are issued right behind the gradient MMAs of problem i: their TMEM
+      // columns are free as soon as the workers have turned S/dP(i) into P/dS(i) (pds_full), so the
+      // workers find the next scores ready when they come back from storing dQ/dK/dV(i).
+      auto issue_scores = [&](int i) {
         const int s = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
-        const uint32_t pi = i & 1;  // phase of the single-stage barriers
-        mbar_wait(&full[s], ph);
-        mbar_wait(t_free, pi ^ 1);
+        mbar_wait(&full[s], (i >> 1) & 1);
         tc_fence_after();
         const uint32_t qa = smem_u32(smem + s * kBwStageBytes);
         const uint32_t ka = qa + kTcTileBytes, va = qa + 2 * kTcTileBytes, doa = qa + 3 * kTcTileBytes;
@@ -478,7 +478,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           umma_bf16(tmem_base + kColDp, make_smem_desc_sw128(doa + k * 32, 16, 1024),
                     make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(sdp_full);
-        mbar_wait(pds_full, pi);
+      };
+      if (n_local > 0) issue_scores(0);
+      for (int i = 0; i < n_local; ++i) {
+        const int s = i & 1;
+        const uint32_t pi = i & 1;  // phase of the single-stage barriers
+        const uint32_t qa = smem_u32(smem + s * kBwStageBytes);
+        const uint32_t ka = qa + kTcTileBytes, doa = qa + 3 * kTcTileBytes;
+        mbar_wait(pds_full, pi);      // P/dS(i) in smem; S/dP(i) consumed
+        mbar_wait(t_free, pi ^ 1);    // dQ/dK/dV(i-1) read out of TMEM
         tc_fence_after();
         const uint32_t pa = smem_u32(p_buf), dsa = smem_u32(ds_buf);
         for (int kk = 0; kk < ksteps; ++kk) {
@@ -499,6 +507,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         }
         umma_commit(grad_full);
         umma_commit(&kv_empty[s]);
+        if (i + 1 < n_local) issue_scores(i + 1);
       }
     }
   } else {
@@ -511,11 +520,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
     const bool warp_stores = q * 32 < p.GL;    // rows beyond the tile's rows have no gradient rows to store
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float scale_log2 = p.scale * 1.4426950408889634f;
-    // 32-column chunks of this warp's column half that its rows' blocks overlap (block-diagonal tile)
+    // The two warps of a lane quarter split the key columns [0, npad) evenly at 16-column
+    // granularity (npad = 96: 48 + 48); of its share a warp visits only the 16-column chunks its
+    // rows' blocks overlap (block-diagonal tile when samples are packed).
     const int blk_lo = PACKED ? min(q * 32, p.GL - 1) / L * L : 0;
     const int blk_hi = PACKED ? min(p.GL, (min(q * 32 + 31, p.GL - 1) / L + 1) * L) : L;
-    const int c_begin = max(half * 64, blk_lo & ~31);
-    const int c_end = min(min(p.npad, half * 64 + 64), (blk_hi + 31) & ~31);
+    const int hsplit = ((p.npad + 31) >> 5) << 4;
+    const int c_begin = max(half * hsplit, blk_lo & ~15);
+    const int c_end = min(min(p.npad, half * hsplit + hsplit), (blk_hi + 15) & ~15);
     auto lse_index = [&](int prob) -> long long {   // lse is [batch, H, L]
       const int n = (prob / H) * p.G + span.sample, h = prob % H;
       return n < p.batch ? ((long long)n * H + h) * L + span.token : -1;
@@ -559,14 +571,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       mbar_wait(sdp_full, pi);
       tc_fence_after();
       if (warp_writes) {
-        for (int c = c_begin; c < c_end; c += 32) {
-          uint32_t sv[32], dv[32];
-          tmem_ld_32x32(t_row + kColS + c, sv);
-          tmem_ld_32x32(t_row + kColDp + c, dv);
+        for (int c = c_begin; c < c_end; c += 16) {
+          uint32_t sv[16], dv[16];
+          tmem_ld_32x16(t_row + kColS + c, sv);
+          tmem_ld_32x16(t_row + kColDp + c, dv);
           tmem_ld_wait();
-          float pr[32], ds[32];
+          float pr[16], ds[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
             const int key = c + j;
             const bool ok = row_ok && (!PACKED || key >= span.lo) && key < span.hi;
             const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[j]), scale_log2, -lse2)) : 0.f;
@@ -574,7 +586,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
             ds[j] = pv * (__uint_as_float(dv[j]) - delta) * p.scale;
           }
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
+          for (int g8 = 0; g8 < 2; ++g8) {
             const uint32_t off = p_tile_off(row, (c >> 3) + g8);
             *reinterpret_cast<uint4*>(p_buf + off) = pack8_bf16(pr + 8 * g8);
             *reinterpret_cast<uint4*>(ds_buf + off) = pack8_bf16(ds + 8 * g8);

@@ -71,10 +71,17 @@ struct GemmSmem {
 // ------------------------------------------------------------------------------------------------
 // activation math (fp32)
 // ------------------------------------------------------------------------------------------------
-// erf-GELU uses the Abramowitz-Stegun 7.1.26 rational/exponential form of erf
-// (|error| <= 1.5e-7, i.e. fp32 round-off; far below the bf16 output resolution): one MUFU.RCP,
-// one MUFU.EX2 and a 5-term Horner chain per element instead of libdevice erff -- with libdevice
-// the epilogue warps, not the tensor pipe, paced the c_fc GEMM (417 TFLOP/s measured, round 1).
+// erf-GELU is evaluated through the lower tail of the standard normal,
+//     q(a) = Phi(-a) = 2^P(-a),   a = min(|x|, 6),
+// with P a degree-6 minimax polynomial of log2 Phi(-a) on [0, 6] (|dP| <= 7.4e-5 in fp32 Horner
+// form, i.e. a RELATIVE error of 5e-5 in q everywhere, 40x below the bf16 half-ulp of the result;
+// beyond 6 the tail is < 1e-9 and the clamp costs nothing):
+//     gelu(x)  = x * Phi(x)          = max(x, 0) - a * q
+//     gelu'(x) = Phi(x) + x * phi(x) = 0.5 + copysign(0.5 - q, x) + x * 0.39894 * 2^(-x^2 log2e / 2)
+// One MUFU.EX2 (two for the derivative) and six FFMA2 per PAIR of elements -- the pair arithmetic
+// uses the packed-fp32 pipe (fma.rn.f32x2), so the 8 epilogue warps spend ~8 issue slots per
+// element instead of the ~19 of the Abramowitz-Stegun rcp/exp form used before (which itself
+// replaced libdevice erff: 417 TFLOP/s, epilogue-bound).
 __device__ __forceinline__ float fast_rcp(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -90,27 +97,37 @@ __device__ __forceinline__ float fast_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// Upper-tail probability of the standard normal at |x| and the Gaussian factor, from the A-S 7.1.26
-// erfc form:  q = Phi(-|x|) = 0.5 * t*(a1 + t*(a2 + ...)) * exp(-x^2/2),  t = 1/(1 + p*|x|/sqrt2).
-// Everything is expressed in z' = |x| * sqrt(log2(e)/2) so that exp(-x^2/2) = 2^(-z'^2) is one
-// FMUL + one MUFU.EX2, and the 0.5 is folded into the coefficients.
-__device__ __forceinline__ void normal_tail(float x, float& q, float& e) {
-  const float zp = fabsf(x) * 0.84932180028801907f;             // |x| * sqrt(log2e / 2)
-  const float t = fast_rcp(fmaf(0.27273748087922250f, zp, 1.0f)); // p / sqrt(log2e)
-  float poly = fmaf(0.5307027145f, t, -0.7265760135f);
-  poly = fmaf(poly, t, 0.7107068705f);
-  poly = fmaf(poly, t, -0.142248368f);
-  poly = fmaf(poly, t, 0.127414796f);
-  e = fast_ex2(-zp * zp);
-  q = poly * t * e;
+// q = Phi(-a) for a pair; `na` = -min(|x|, 6)
+__device__ __forceinline__ float2 normal_tail2(float2 na) {
+  float2 acc = fma2(splat2(2.343321648e-05f), na, splat2(6.197391776e-04f));
+  acc = fma2(acc, na, splat2(7.260354701e-03f));
+  acc = fma2(acc, na, splat2(5.141863227e-02f));
+  acc = fma2(acc, na, splat2(-4.608635008e-01f));
+  acc = fma2(acc, na, splat2(1.150480390e+00f));
+  acc = fma2(acc, na, splat2(-1.0f));
+  return make_float2(fast_ex2(acc.x), fast_ex2(acc.y));
+}
+__device__ __forceinline__ float2 neg_abs_clamped2(float2 x) {
+  return make_float2(fmaxf(-fabsf(x.x), -6.0f), fmaxf(-fabsf(x.y), -6.0f));
+}
+__device__ __forceinline__ float2 gelu_erf_fwd2(float2 x) {
+  const float2 na = neg_abs_clamped2(x);
+  const float2 q = normal_tail2(na);
+  return fma2(na, q, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
+__device__ __forceinline__ float2 gelu_erf_bwd2(float2 x) {
+  const float2 na = neg_abs_clamped2(x);
+  const float2 q = normal_tail2(na);
+  const float2 t = mul2(mul2(x, splat2(-0.72134752044448170f)), x);          // -x^2 * log2(e) / 2
+  const float2 e = make_float2(fast_ex2(t.x), fast_ex2(t.y));
+  const float2 h = fma2(q, splat2(-1.0f), splat2(0.5f));                       // 0.5 - q  (>= 0)
+  const float2 hs = make_float2(__uint_as_float(__float_as_uint(h.x) | (__float_as_uint(x.x) & 0x80000000u)),
+                                __uint_as_float(__float_as_uint(h.y) | (__float_as_uint(x.y) & 0x80000000u)));
+  const float2 d = fma2(mul2(x, e), splat2(0.3989422804014327f), hs);
+  return add2(d, splat2(0.5f));
 }
 __device__ __forceinline__ float act_fwd(float x, int act) {
-  if (act == 0) {  // x * Phi(x)
-    float q, e;
-    normal_tail(x, q, e);
-    const float r = x * q;
-    return x >= 0.f ? x - r : r;
-  }
+  if (act == 0) return gelu_erf_fwd2(make_float2(x, x)).x;
   if (act == 1) {
     const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
     return 0.5f * x * (1.0f + fast_tanh(u));
@@ -118,12 +135,7 @@ __device__ __forceinline__ float act_fwd(float x, int act) {
   return x * fast_rcp(1.0f + fast_ex2(-1.702f * 1.4426950408889634f * x));
 }
 __device__ __forceinline__ float act_bwd(float x, int act) {
-  if (act == 0) {  // Phi(x) + x * phi(x)
-    float q, e;
-    normal_tail(x, q, e);
-    const float cdf = x >= 0.f ? 1.0f - q : q;
-    return fmaf(x * 0.3989422804014327f, e, cdf);
-  }
+  if (act == 0) return gelu_erf_bwd2(make_float2(x, x)).x;
   if (act == 1) {
     const float x2 = x * x;
     const float u = 0.7978845608028654f * fmaf(0.044715f * x2, x, x);
@@ -293,7 +305,9 @@ __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = *reinterpret_cast<const float4*>(sb + j);
-        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+        const float2 lo = add2(make_float2(f[j], f[j + 1]), make_float2(b.x, b.y));
+        const float2 hi = add2(make_float2(f[j + 2], f[j + 3]), make_float2(b.z, b.w));
+        f[j] = lo.x; f[j + 1] = lo.y; f[j + 2] = hi.x; f[j + 3] = hi.y;
       }
     }
     if (p.aux) {
@@ -305,7 +319,11 @@ __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[
     }
     if (p.act == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 0);
+      for (int j = 0; j < 32; j += 2) {
+        const float2 g = gelu_erf_fwd2(make_float2(f[j], f[j + 1]));
+        f[j] = g.x;
+        f[j + 1] = g.y;
+      }
     } else if (p.act == 1) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], 1);
@@ -319,7 +337,11 @@ __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[
     unpack_bf16x32(side, a);   // rows >= M carry zeros: their result is clipped by the TMA store
     if (p.act == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 0);
+      for (int j = 0; j < 32; j += 2) {
+        const float2 g = mul2(make_float2(f[j], f[j + 1]), gelu_erf_bwd2(make_float2(a[j], a[j + 1])));
+        f[j] = g.x;
+        f[j + 1] = g.y;
+      }
     } else if (p.act == 1) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 1);
@@ -346,10 +368,14 @@ __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[
 
 // One accumulator stage's worth of store-type epilogue for one warp: `ncols` columns starting at
 // tile-local column `col_local0`; TMEM loads and the side-operand loads run one chunk ahead.
-template <int EPI>
+// `release()` hands the accumulator stage back to the MMA issuer; it is called as soon as the LAST
+// chunk sits in registers, so the next-but-one tile's MMAs start while this warp is still doing the
+// math and the stores of its final chunk.
+template <int EPI, class Release>
 __device__ __forceinline__ void epi_run_store(const GemmParams& p, uint32_t t_warp, long long row, bool row_ok,
                                               int tile_col0, int col_local0, int ncols, const float* sbias_tile,
-                                              const CUtensorMap* tm_c, const CUtensorMap* tm_aux, uint8_t* sbuf) {
+                                              const CUtensorMap* tm_c, const CUtensorMap* tm_aux, uint8_t* sbuf,
+                                              Release release) {
   const int row0_warp = static_cast<int>(row) - static_cast<int>(threadIdx.x & 31);
   long long side_ld;
   const __nv_bfloat16* side_base = epi_side_ptr<EPI>(p, side_ld);
@@ -386,6 +412,8 @@ __device__ __forceinline__ void epi_run_store(const GemmParams& p, uint32_t t_wa
 #pragma unroll
         for (int i = 0; i < 4; ++i) side_next[i] = make_uint4(0, 0, 0, 0);
       }
+    } else {
+      release();
     }
     if (col0 >= p.N) continue;  // warp-uniform
     epi_apply_store<EPI>(p, f, row, row_ok, col0, sbias_tile + col_local0 + c * 32, side, tm_c, tm_aux, sbuf,
@@ -581,7 +609,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t t_warp = tmem_base + acc * BN + half * kColsPerWarp + (static_cast<uint32_t>(q * 32) << 16);
         if constexpr (EPI <= EPI_ATOMIC_F32) {
           epi_run_store<EPI>(p, t_warp, row, row_ok, n_blk * BN, half * kColsPerWarp, kColsPerWarp, sbias_tile,
-                             &tmap_c, &tmap_aux, smem + S::kStoreOffset + ew * 2048);
+                             &tmap_c, &tmap_aux, smem + S::kStoreOffset + ew * 2048, [&]() {
+                               tc_fence_before();
+                               __syncwarp();
+                               if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                             });
         } else {
         uint32_t vnext[32];
         tmem_ld_32x32(t_warp, vnext);
@@ -636,11 +668,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
-        }  // contrastive-head epilogues
-        // all of this warp's TMEM reads for the stage are complete (wait::ld above)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          // all of this warp's TMEM reads for the stage are complete (wait::ld above)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }  // contrastive-head epilogues (the store-type epilogues release the stage themselves)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
 

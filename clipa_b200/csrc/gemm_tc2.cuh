@@ -217,10 +217,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_after();
       const uint32_t t_warp = tmem_base + acc * kBN2 + half * kColsPerWarp + (static_cast<uint32_t>(q * 32) << 16);
       epi_run_store<EPI>(p, t_warp, row, row_ok, n_blk * kBN2, half * kColsPerWarp, kColsPerWarp, sbias_tile,
-                         &tmap_c, &tmap_aux, smem + kStoreOffset2 + ew * 2048);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_addr(smem_u32(&tmem_empty[acc])));
+                         &tmap_c, &tmap_aux, smem + kStoreOffset2 + ew * 2048, [&]() {
+                           tc_fence_before();
+                           __syncwarp();
+                           if (lane == 0) mbar_arrive_cluster(leader_addr(smem_u32(&tmem_empty[acc])));
+                         });
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
