@@ -387,6 +387,34 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, uint32_t ta
   }
 }
 
+// dQ, dK, dV: 32 fp32 columns of one TMEM row each -> three 64-byte bf16 row segments; the three
+// TMEM loads are in flight together (one wait)
+__device__ __forceinline__ void store_grad_rows(__nv_bfloat16* drow, int D, uint32_t t_row, uint32_t col_dq,
+                                                uint32_t col_dk, uint32_t col_dv, int c0, bool ok) {
+  uint32_t a[32], b[32], c[32];
+  tmem_ld_32x32(t_row + col_dq + c0, a);
+  tmem_ld_32x32(t_row + col_dk + c0, b);
+  tmem_ld_32x32(t_row + col_dv + c0, c);
+  tmem_ld_wait();
+  if (ok) {
+    auto put = [&](__nv_bfloat16* dst, const uint32_t (&v)[32]) {
+      uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {
+        uint4 t;
+        t.x = pack_bf16x2(__uint_as_float(v[8 * g8]), __uint_as_float(v[8 * g8 + 1]));
+        t.y = pack_bf16x2(__uint_as_float(v[8 * g8 + 2]), __uint_as_float(v[8 * g8 + 3]));
+        t.z = pack_bf16x2(__uint_as_float(v[8 * g8 + 4]), __uint_as_float(v[8 * g8 + 5]));
+        t.w = pack_bf16x2(__uint_as_float(v[8 * g8 + 6]), __uint_as_float(v[8 * g8 + 7]));
+        d4[g8] = t;
+      }
+    };
+    put(drow, a);
+    put(drow + D, b);
+    put(drow + 2 * D, c);
+  }
+}
+
 template <bool CAUSAL, bool PACKED>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
@@ -532,10 +560,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const int n = (prob / H) * p.G + span.sample, h = prob % H;
       return n < p.batch ? ((long long)n * H + h) * L + span.token : -1;
     };
-    float lse2_next = 0.f;
+    // the next problem's lse (one float per thread) is loaded a whole problem ahead and only
+    // touched (scaled) where it is used, so the global-load latency never sits on the critical path
+    float lse_raw = 0.f;
     if (n_local > 0 && row_in_tile) {
       const long long li = lse_index(blockIdx.x);
-      if (li >= 0) lse2_next = p.lse[li] * 1.4426950408889634f;
+      if (li >= 0) lse_raw = p.lse[li];
     }
     for (int i = 0; i < n_local; ++i) {
       const int s = i & 1;
@@ -544,11 +574,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       const int prob = blockIdx.x + i * gridDim.x;
       const int n = (prob / H) * p.G, h = prob % H;
       const bool row_ok = row_in_tile && n + span.sample < p.batch;
-      const float lse2 = lse2_next;
-      if (i + 1 < n_local && row_in_tile) {  // prefetch the next problem's lse (one float per thread)
-        const long long li = lse_index(prob + (int)gridDim.x);
-        lse2_next = li >= 0 ? p.lse[li] * 1.4426950408889634f : 0.f;
-      }
       // delta_i = sum_d dO_id * O_id from the swizzled smem tiles (TMA already landed them)
       mbar_wait(&full[s], ph);
       float delta = 0.f;
@@ -570,6 +595,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       }
       mbar_wait(sdp_full, pi);
       tc_fence_after();
+      const float lse2 = lse_raw * 1.4426950408889634f;
+      if (i + 1 < n_local && row_in_tile) {
+        const long long li = lse_index(prob + (int)gridDim.x);
+        lse_raw = li >= 0 ? p.lse[li] : 0.f;
+      }
       if (warp_writes) {
         for (int c = c_begin; c < c_end; c += 16) {
           uint32_t sv[16], dv[16];
@@ -603,9 +633,255 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       if (warp_stores) {
         __nv_bfloat16* drow = p.dqkv + ((long long)n * L + row) * pitch + h * kTcHd;
         const int c0 = half * 32;
-        store_row32_bf16(drow, t_row + kColDq, c0, row_ok);              // dQ[row, :]
-        store_row32_bf16(drow + D, t_row + kColDk, c0, row_ok);          // dK[row, :]  (row = key index)
-        store_row32_bf16(drow + 2 * D, t_row + kColDv, c0, row_ok);      // dV[row, :]
+        store_grad_rows(drow, D, t_row, kColDq, kColDk, kColDv, c0, row_ok);   // rows of dQ, dK (row = key), dV
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ================================================================================================
+// BACKWARD, software-pipelined variant for 64 < L <= 96 (one sample per tile; ViT towers at 65 / 82
+// tokens).  Same math and warp roles as attn_bwd_tc_kernel, but the tiles are 96 rows tall
+// (12 KB), which leaves room for TWO P/dS buffers next to the 2-stage operand ring, and the
+// worker loop is skewed by one problem:
+//     workers:  ... | P/dS(i+1) from S/dP(i+1) | store dQ/dK/dV(i) | P/dS(i+2) | store (i+1) | ...
+//     tensor :  ... | S,dP(i+2) | dV,dK,dQ(i+1) | S,dP(i+3) | dV,dK,dQ(i+2) | ...
+// so the gradient MMAs of problem i run while the workers are busy with the scores of problem
+// i+1, and the scores of problem i+2 are in TMEM before the workers ask for them.  Neither the MMA
+// latency nor the barrier round trips sit on the workers' critical path any more (in the
+// unpipelined kernel the workers spent 28 % of their time waiting for the gradient MMAs and 9 % for
+// the scores; ncu source view, profiles/).
+// The M = 128 MMAs read 32 rows past the 96-row A tiles; those accumulator rows (TMEM lanes
+// 96..127) are never read.
+// ================================================================================================
+constexpr int kPRows = 96;
+constexpr int kPTile = kPRows * 128;                              // 12 KB
+constexpr int kPStage = kBwTiles * kPTile;                        // Q, K, V, dO, O
+constexpr int kPPds = 2 * kPTile;                                 // one P (or dS) buffer: 2 key atoms
+// Layout: [P0 dS0 P1 dS1 | stage 0 | stage 1 | barriers].  The P/dS buffers come first so that the
+// 32-row over-read of the last dS atom lands in the operand ring, not past the allocation.
+constexpr int kPPOff = 0;                                         // P/dS buffer b at b * 2 * kPPds
+constexpr int kPStageOff = 4 * kPPds;
+constexpr int kPSmemBar = kPStageOff + 2 * kPStage;
+constexpr int kPSmemTotal = kPSmemBar + 256 + 1024;
+static_assert(kPSmemTotal <= 227 * 1024, "pipelined attention backward shared memory budget");
+
+__device__ __forceinline__ uint32_t p96_tile_off(int row, int chunk) {
+  return (chunk >> 3) * kPTile + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+}
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                        const __grid_constant__ CUtensorMap tmap_o, const AttnBwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPSmemBar);
+  uint64_t* full = bars;           // [2] TMA landed
+  uint64_t* kv_empty = bars + 2;   // [2] smem stage free
+  uint64_t* sdp_full = bars + 4;   // S and dP in TMEM
+  uint64_t* pds_full = bars + 5;   // [2] P and dS buffer b written (8 warp arrivals)
+  uint64_t* grad_full = bars + 7;  // dQ, dK, dV in TMEM
+  uint64_t* t_free = bars + 8;     // dQ/dK/dV read out of TMEM (8 warp arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.L, H = p.H, D = H * kTcHd;
+  const int total = p.batch * H;
+  const long long pitch = 3LL * D;
+
+  for (int i = threadIdx.x; i < kPSmemBar / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_o);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&pds_full[i], 8);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(grad_full, 1);
+    mbar_init(t_free, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  constexpr uint32_t kColS = 0, kColDp = 128, kColDq = 256, kColDk = 320, kColDv = 384;
+
+  const int n_local = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_local; ++i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        const int prob = blockIdx.x + i * gridDim.x;
+        const int n = prob / H, h = prob - n * H;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        uint8_t* st = smem + kPStageOff + s * kPStage;
+        mbar_expect_tx(&full[s], (uint32_t)kBwTiles * (uint32_t)L * 128u);
+        tma_load_2d(st, &tmap_qkv, &full[s], h * kTcHd, n * L);
+        tma_load_2d(st + kPTile, &tmap_qkv, &full[s], D + h * kTcHd, n * L);
+        tma_load_2d(st + 2 * kPTile, &tmap_qkv, &full[s], 2 * D + h * kTcHd, n * L);
+        tma_load_2d(st + 3 * kPTile, &tmap_do, &full[s], h * kTcHd, n * L);
+        tma_load_2d(st + 4 * kPTile, &tmap_o, &full[s], h * kTcHd, n * L);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.npad, false, false);   // A K-major, B K-major
+      const uint32_t idesc_t = make_idesc_bf16(128, kTcHd, true, true);                // A MN (P^T/dS^T), B MN
+      const uint32_t idesc_q = make_idesc_bf16(128, kTcHd, false, true);               // A K (dS), B MN (K)
+      const int ksteps = p.npad / 16;
+      auto issue_scores = [&](int i) {
+        const int s = i & 1;
+        mbar_wait(&full[s], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(smem + kPStageOff + s * kPStage);
+        const uint32_t ka = qa + kPTile, va = qa + 2 * kPTile, doa = qa + 3 * kPTile;
+#pragma unroll
+        for (int k = 0; k < kTcHd / 16; ++k)
+          umma_bf16(tmem_base + kColS, make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                    make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kTcHd / 16; ++k)
+          umma_bf16(tmem_base + kColDp, make_smem_desc_sw128(doa + k * 32, 16, 1024),
+                    make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+      };
+      if (n_local > 0) issue_scores(0);
+      for (int i = 0; i < n_local; ++i) {
+        const int s = i & 1;
+        mbar_wait(&pds_full[s], (i >> 1) & 1);   // P/dS(i) in buffer s; S/dP(i) consumed
+        tc_fence_after();
+        if (i + 1 < n_local) issue_scores(i + 1);
+        mbar_wait(t_free, (i & 1) ^ 1);          // dQ/dK/dV(i-1) read out of TMEM
+        tc_fence_after();
+        const uint32_t qa = smem_u32(smem + kPStageOff + s * kPStage);
+        const uint32_t ka = qa + kPTile, doa = qa + 3 * kPTile;
+        const uint32_t pa = smem_u32(smem + kPPOff + s * 2 * kPPds), dsa = pa + kPPds;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          // contraction over queries: A = P^T / dS^T (MN-major view of the [query][key] tiles: key
+          // atoms one tile apart = LBO, 8-query groups 1 KB apart = SBO), B = dO / Q MN-major
+          const uint64_t a_p = make_smem_desc_sw128(pa + kk * 2048, kPTile, 1024);
+          const uint64_t a_ds = make_smem_desc_sw128(dsa + kk * 2048, kPTile, 1024);
+          const uint64_t b_do = make_smem_desc_sw128(doa + kk * 2048, 8192, 1024);
+          const uint64_t b_q = make_smem_desc_sw128(qa + kk * 2048, 8192, 1024);
+          umma_bf16(tmem_base + kColDv, a_p, b_do, idesc_t, kk > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + kColDk, a_ds, b_q, idesc_t, kk > 0 ? 1u : 0u);
+        }
+        for (int kk = 0; kk < ksteps; ++kk) {
+          // contraction over keys: A = dS K-major, B = K MN-major
+          const uint64_t a_ds = make_smem_desc_sw128(dsa + (kk >> 2) * kPTile + (kk & 3) * 32, 16, 1024);
+          const uint64_t b_k = make_smem_desc_sw128(ka + kk * 2048, 8192, 1024);
+          umma_bf16(tmem_base + kColDq, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(grad_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;     // which half of the columns
+    const int row = q * 32 + lane;        // query index (scores stage) / key index (dK, dV rows)
+    const bool row_ok = row < L;
+    const bool warp_writes = q * 32 < p.npad;  // rows >= npad are never contracted: skip their P/dS
+    const bool warp_stores = q * 32 < L;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float scale_log2 = p.scale * 1.4426950408889634f;
+    const int hsplit = ((p.npad + 31) >> 5) << 4;          // 96 keys: 48 + 48
+    const int c_begin = half * hsplit;
+    const int c_end = min(p.npad, c_begin + hsplit);
+    const int hi = CAUSAL ? row + 1 : L;                   // valid keys [0, hi)
+
+    float lse_raw = 0.f;
+    if (n_local > 0 && row_ok) lse_raw = p.lse[(long long)blockIdx.x * L + row];   // lse is [batch, H, L]
+
+    // scores stage of problem j: S/dP (TMEM) -> P/dS (bf16, swizzled smem buffer j & 1)
+    auto scores_stage = [&](int j) {
+      const int s = j & 1;
+      const int prob = blockIdx.x + j * gridDim.x;
+      mbar_wait(&full[s], (j >> 1) & 1);
+      float delta = 0.f;
+      if (row_ok && c_begin < c_end) {   // delta = sum_d dO * O from the swizzled smem tiles
+        const uint8_t* dot = smem + kPStageOff + s * kPStage + 3 * kPTile + row * 128;
+        const uint8_t* ot = dot + kPTile;
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t off = ((c ^ (row & 7)) << 4);
+          const uint4 a = *reinterpret_cast<const uint4*>(ot + off);
+          const uint4 b = *reinterpret_cast<const uint4*>(dot + off);
+          d4[0] = fmaf(bf16lo(a.x), bf16lo(b.x), fmaf(bf16hi(a.x), bf16hi(b.x), d4[0]));
+          d4[1] = fmaf(bf16lo(a.y), bf16lo(b.y), fmaf(bf16hi(a.y), bf16hi(b.y), d4[1]));
+          d4[2] = fmaf(bf16lo(a.z), bf16lo(b.z), fmaf(bf16hi(a.z), bf16hi(b.z), d4[2]));
+          d4[3] = fmaf(bf16lo(a.w), bf16lo(b.w), fmaf(bf16hi(a.w), bf16hi(b.w), d4[3]));
+        }
+        delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+      }
+      mbar_wait(sdp_full, j & 1);
+      tc_fence_after();
+      const float lse2 = lse_raw * 1.4426950408889634f;
+      if (j + 1 < n_local && row_ok)   // next problem's lse: consumed one whole stage later
+        lse_raw = p.lse[(long long)(prob + (int)gridDim.x) * L + row];
+      if (warp_writes) {
+        uint8_t* p_buf = smem + kPPOff + s * 2 * kPPds;
+        uint8_t* ds_buf = p_buf + kPPds;
+        for (int c = c_begin; c < c_end; c += 16) {
+          uint32_t sv[16], dv[16];
+          tmem_ld_32x16(t_row + kColS + c, sv);
+          tmem_ld_32x16(t_row + kColDp + c, dv);
+          tmem_ld_wait();
+          float pr[16], ds[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const bool ok = row_ok && (c + jj) < hi;
+            const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[jj]), scale_log2, -lse2)) : 0.f;
+            pr[jj] = pv;
+            ds[jj] = pv * (__uint_as_float(dv[jj]) - delta) * p.scale;
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            const uint32_t off = p96_tile_off(row, (c >> 3) + g8);
+            *reinterpret_cast<uint4*>(p_buf + off) = pack8_bf16(pr + 8 * g8);
+            *reinterpret_cast<uint4*>(ds_buf + off) = pack8_bf16(ds + 8 * g8);
+          }
+        }
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full[s]);
+    };
+
+    if (n_local > 0) scores_stage(0);
+    for (int i = 0; i < n_local; ++i) {
+      if (i + 1 < n_local) scores_stage(i + 1);
+      // ---- gradients of problem i: this warp stores 32 of the 64 columns of each row
+      const int prob = blockIdx.x + i * gridDim.x;
+      const int n = prob / H, h = prob - n * H;
+      mbar_wait(grad_full, i & 1);
+      tc_fence_after();
+      if (warp_stores) {
+        __nv_bfloat16* drow = p.dqkv + ((long long)n * L + row) * pitch + h * kTcHd;
+        store_grad_rows(drow, D, t_row, kColDq, kColDk, kColDv, half * 32, row_ok);
       }
       tc_fence_before();
       __syncwarp();
@@ -626,6 +902,35 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const f
   CLIPA_REQUIRE(L >= 1 && L <= 128, CLIPA_ERR_UNSUPPORTED, "attention_bwd_tc: L=%d > 128", L);
   const int D = H * kTcHd;
   CUtensorMap tq, td, to;
+  if (L > 64 && L <= kPRows) {   // one sample per tile and it fits 96-row tiles: pipelined kernel
+    int rc = encode_tmap_2d_bf16(&tq, qkv, (uint64_t)3 * D, (uint64_t)batch * L, (uint64_t)3 * D * 2, kTcHd,
+                                 (uint32_t)L);
+    if (rc) return rc;
+    rc = encode_tmap_2d_bf16(&td, dout, (uint64_t)D, (uint64_t)batch * L, (uint64_t)D * 2, kTcHd, (uint32_t)L);
+    if (rc) return rc;
+    rc = encode_tmap_2d_bf16(&to, out, (uint64_t)D, (uint64_t)batch * L, (uint64_t)D * 2, kTcHd, (uint32_t)L);
+    if (rc) return rc;
+    AttnBwParams p;
+    p.lse = lse;
+    p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+    p.L = L; p.H = H; p.batch = batch;
+    p.G = 1; p.GL = L;
+    p.npad = (L + 15) & ~15;
+    p.scale = 1.0f / sqrtf((float)kTcHd);
+    long long total = (long long)batch * H;
+    int grid = num_sms();
+    if (grid > total) grid = (int)total;
+    auto launch = [&](auto kern) -> int {
+      CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemTotal));
+      kern<<<grid, kTcThreads, kPSmemTotal, stream>>>(tq, td, to, p);
+      return CLIPA_OK;
+    };
+    const int lrc = causal ? launch(attn_bwd_tc_pipe_kernel<true>) : launch(attn_bwd_tc_pipe_kernel<false>);
+    if (lrc) return lrc;
+    CLIPA_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return CLIPA_OK;
+  }
   const int G = 128 / L, GL = G * L;
   int rc = encode_tmap_2d_bf16(&tq, qkv, (uint64_t)3 * D, (uint64_t)batch * L, (uint64_t)3 * D * 2, kTcHd,
                                (uint32_t)GL);

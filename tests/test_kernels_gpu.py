@@ -156,7 +156,10 @@ def test_colsum(dev):
                                              # tile, blocks straddling 32-column chunks, G*L < 128, one sample
                                              (19, 16, 12, 64, True), (21, 16, 4, 64, False), (9, 8, 16, 64, True),
                                              (7, 33, 4, 64, True), (5, 48, 2, 64, False), (11, 63, 2, 64, True),
-                                             (300, 16, 12, 64, True), (3, 64, 2, 64, False), (1, 5, 2, 64, True)])
+                                             (300, 16, 12, 64, True), (3, 64, 2, 64, False), (1, 5, 2, 64, True),
+                                             # pipelined backward (64 < L <= 96), several problems per CTA
+                                             (40, 82, 16, 64, False), (37, 96, 8, 64, True), (3, 70, 4, 64, True),
+                                             (75, 65, 4, 64, False)])
 def test_attention(dev, B, L, H, hd, causal):
     o = ops()
     torch.manual_seed(B * 100 + L)
