@@ -10,7 +10,8 @@
 
 namespace clipa {
 
-constexpr int kLnWarps = 8;  // warps (rows in flight) per block
+constexpr int kLnWarps = 8;      // forward / colsum: warps per block (2 blocks per SM)
+constexpr int kLnBwdWarps = 12;  // backward: one 12-warp block per SM (170 registers per thread, no spills)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -29,65 +30,144 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return t;
 }
 
-// VPL = 16-byte vectors per lane (D <= 256*VPL)
-template <int VPL>
-__global__ void __launch_bounds__(kLnWarps * 32)
+// ---- packed-pair helpers: a 16-byte vector of 8 bf16 <-> four float2; all row arithmetic runs on
+// the packed-fp32 pipe (FADD2 / FMUL2 / FFMA2), which halves the issue slots per element -- with
+// scalar fp32 math these kernels were issue-bound at ~55-60 % of the HBM roofline.
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ void unpack8p(const uint4& t, float2 (&f)[4]) {
+  f[0] = bf2_to_f2(t.x); f[1] = bf2_to_f2(t.y); f[2] = bf2_to_f2(t.z); f[3] = bf2_to_f2(t.w);
+}
+__device__ __forceinline__ uint4 pack8p(const float2 (&f)[4]) {
+  uint4 t;
+  t.x = pack_bf16x2(f[0].x, f[0].y); t.y = pack_bf16x2(f[1].x, f[1].y);
+  t.z = pack_bf16x2(f[2].x, f[2].y); t.w = pack_bf16x2(f[3].x, f[3].y);
+  return t;
+}
+// Affine parameters in shared memory, split so that a lane's two float4 halves of its 8 columns sit
+// in separate arrays (16-byte lane stride: conflict-free LDS.128):  lo[vi] = p[8vi..8vi+3],
+// hi[vi] = p[8vi+4..8vi+7].
+__device__ __forceinline__ void stage_param(float4* lo, float4* hi, const float* __restrict__ p, int nvec) {
+  for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    lo[vi] = __ldg(reinterpret_cast<const float4*>(p) + 2 * vi);
+    hi[vi] = __ldg(reinterpret_cast<const float4*>(p) + 2 * vi + 1);
+  }
+}
+__device__ __forceinline__ void load_param(const float4* lo, const float4* hi, int vi, float2 (&g)[4]) {
+  const float4 a = lo[vi], b = hi[vi];
+  g[0] = make_float2(a.x, a.y); g[1] = make_float2(a.z, a.w);
+  g[2] = make_float2(b.x, b.y); g[3] = make_float2(b.z, b.w);
+}
+
+// Forward.  VPL = 16-byte vectors per lane (D <= 256*VPL).  A warp normalises TWO adjacent rows per
+// iteration: eight 16-byte loads per lane are in flight before the first reduction, the two
+// shuffle-reduction chains interleave, and every gamma/beta vector read from shared memory serves
+// both rows.
+template <int VPL, bool FULL>   // FULL: D == 256 * VPL, no column predicates
+__global__ void __launch_bounds__(kLnWarps * 32, 2)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
               float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int D,
               float eps) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ float4 ln_smem4[];
   const int nvec = D >> 3;
+  float4* g_lo = ln_smem4;
+  float4* g_hi = g_lo + nvec;
+  float4* b_lo = g_hi + nvec;
+  float4* b_hi = b_lo + nvec;
+  stage_param(g_lo, g_hi, gamma, nvec);
+  stage_param(b_lo, b_hi, beta, nvec);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   const long long warp_stride = (long long)gridDim.x * kLnWarps;
   const float inv_d = 1.0f / (float)D;
-  for (long long row = warp_global; row < rows; row += warp_stride) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
-    float v[VPL][8];
-    float s = 0.f;
+  for (long long pair = warp_global; 2 * pair < rows; pair += warp_stride) {
+    const long long row0 = 2 * pair;
+    const bool two = row0 + 1 < rows;
+    const long long row1 = two ? row0 + 1 : row0;
+    const uint4* xr0 = reinterpret_cast<const uint4*>(x + row0 * D);
+    const uint4* xr1 = reinterpret_cast<const uint4*>(x + row1 * D);
+    uint4 p0[VPL], p1[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
-      if (vi < nvec) {
-        uint4 t = __ldg(xr + vi);
-        unpack8(t, v[i]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[i][j];
+      if (FULL || vi < nvec) {
+        p0[i] = __ldg(xr0 + vi);
+        p1[i] = __ldg(xr1 + vi);
       }
     }
-    const float mean = warp_sum(s) * inv_d;
-    float sq = 0.f;
+    float2 v0[VPL][4], v1[VPL][4];
+    float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      if (lane + 32 * i < nvec) {
+      if (FULL || lane + 32 * i < nvec) {
+        unpack8p(p0[i], v0[i]);
+        unpack8p(p1[i], v1[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = v[i][j] - mean;
-          sq += d * d;
+        for (int j = 0; j < 4; ++j) {
+          s0 = add2(s0, v0[i][j]);
+          s1 = add2(s1, v1[i][j]);
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
-    uint4* yr = reinterpret_cast<uint4*>(y + row * D);
+    float a0 = s0.x + s0.y, a1 = s1.x + s1.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    const float mean0 = a0 * inv_d, mean1 = a1 * inv_d;
+    const float2 nm0 = splat2(-mean0), nm1 = splat2(-mean1);
+    float2 q0 = make_float2(0.f, 0.f), q1 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (FULL || lane + 32 * i < nvec) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v0[i][j] = add2(v0[i][j], nm0);
+          v1[i][j] = add2(v1[i][j], nm1);
+          q0 = fma2(v0[i][j], v0[i][j], q0);
+          q1 = fma2(v1[i][j], v1[i][j], q1);
+        }
+      }
+    }
+    a0 = q0.x + q0.y;
+    a1 = q1.x + q1.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    const float rstd0 = rsqrtf(a0 * inv_d + eps), rstd1 = rsqrtf(a1 * inv_d + eps);
+    const float2 r0 = splat2(rstd0), r1 = splat2(rstd1);
+    uint4* yr0 = reinterpret_cast<uint4*>(y + row0 * D);
+    uint4* yr1 = reinterpret_cast<uint4*>(y + row1 * D);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
-      if (vi < nvec) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi);
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float o[8];
+      if (FULL || vi < nvec) {
+        float2 g[4], b[4], o0[4], o1[4];
+        load_param(g_lo, g_hi, vi, g);
+        load_param(b_lo, b_hi, vi, b);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
-        yr[vi] = pack8(o);
+        for (int j = 0; j < 4; ++j) {
+          o0[j] = fma2(mul2(v0[i][j], r0), g[j], b[j]);
+          o1[j] = fma2(mul2(v1[i][j], r1), g[j], b[j]);
+        }
+        yr0[vi] = pack8p(o0);
+        if (two) yr1[vi] = pack8p(o1);
       }
     }
     if (lane == 0 && mean_out) {
-      mean_out[row] = mean;
-      rstd_out[row] = rstd;
+      mean_out[row0] = mean0;
+      rstd_out[row0] = rstd0;
+      if (two) {
+        mean_out[row1] = mean1;
+        rstd_out[row1] = rstd1;
+      }
     }
   }
 }
@@ -96,97 +176,110 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 //   dx = rstd * (g - mean_D(g) - xhat * mean_D(g*xhat)) (+ dres)
 //   dgamma += sum_rows dy*xhat ;  dbeta += sum_rows dy
 // Each warp keeps its dgamma/dbeta partials in registers over its grid-stride rows; the block
-// reduces them through shared memory and issues one red.add per column per block.  To keep the
-// register footprint low enough for 2 blocks/SM the row is held PACKED (bf16x2) between the
-// statistics pass and the output pass, and gamma is read from shared memory.
-template <int VPL>
-__global__ void __launch_bounds__(kLnWarps * 32, 2)
+// reduces them through shared memory and issues one red.add per column per block.  The row is
+// held PACKED (bf16x2) between the statistics pass and the output pass and gamma is read from
+// shared memory; one 12-warp block per SM gives each thread 170 registers (64 of them partials).
+template <int VPL, bool FULL>
+__global__ void __launch_bounds__(kLnBwdWarps * 32, 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
               __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
               long long rows, int D) {
-  extern __shared__ float red[];  // [D] gamma, then [kLnWarps][2][D] reduction scratch
-  float* sgam = red;
-  float* scratch = red + D;
+  extern __shared__ float4 ln_smem4[];  // gamma (split halves), then [kLnBwdWarps][2][D] reduction scratch
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nvec = D >> 3;
-  const long long warp_global = (long long)blockIdx.x * kLnWarps + warp;
-  const long long warp_stride = (long long)gridDim.x * kLnWarps;
+  float4* g_lo = ln_smem4;
+  float4* g_hi = g_lo + nvec;
+  float* scratch = reinterpret_cast<float*>(g_hi + nvec);
+  const long long warp_global = (long long)blockIdx.x * kLnBwdWarps + warp;
+  const long long warp_stride = (long long)gridDim.x * kLnBwdWarps;
   const float inv_d = 1.0f / (float)D;
 
-  for (int c = threadIdx.x; c < D; c += blockDim.x) sgam[c] = gamma[c];
+  stage_param(g_lo, g_hi, gamma, nvec);
   __syncthreads();
 
-  float acc_g[VPL][8], acc_b[VPL][8];
+  float2 acc_g[VPL][4], acc_b[VPL][4];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc_g[i][j] = 0.f; acc_b[i][j] = 0.f; }
+    for (int j = 0; j < 4; ++j) { acc_g[i][j] = make_float2(0.f, 0.f); acc_b[i][j] = make_float2(0.f, 0.f); }
   }
 
   for (long long row = warp_global; row < rows; row += warp_stride) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + row * D);
+    const uint4* rr = reinterpret_cast<const uint4*>(dres ? dres + row * D : x);
     const float mean = mean_in[row];
     const float rstd = rstd_in[row];
-    uint4 xp[VPL], dp[VPL];
-    float s1 = 0.f, s2 = 0.f;
+    uint4 xp[VPL], dp[VPL], rp[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
-      if (vi < nvec) {
+      if (FULL || vi < nvec) {
         xp[i] = __ldg(xr + vi);
         dp[i] = __ldg(dyr + vi);
       }
     }
+    const float2 r2 = splat2(rstd), nmr = splat2(-mean * rstd);
+    float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
-      if (vi < nvec) {
-        float xv[8], dv[8];
-        unpack8(xp[i], xv);
-        unpack8(dp[i], dv);
-        const float4 g0 = *reinterpret_cast<const float4*>(sgam + vi * 8);
-        const float4 g1 = *reinterpret_cast<const float4*>(sgam + vi * 8 + 4);
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      if (FULL || vi < nvec) {
+        float2 xv[4], dv[4], gm[4];
+        unpack8p(xp[i], xv);
+        unpack8p(dp[i], dv);
+        load_param(g_lo, g_hi, vi, gm);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[j] - mean) * rstd;
-          const float g = dv[j] * gm[j];
-          s1 += g;
-          s2 = fmaf(g, xh, s2);
-          acc_g[i][j] = fmaf(dv[j], xh, acc_g[i][j]);
-          acc_b[i][j] += dv[j];
+        for (int j = 0; j < 4; ++j) {
+          const float2 xh = fma2(xv[j], r2, nmr);
+          const float2 g = mul2(dv[j], gm[j]);
+          s1 = add2(s1, g);
+          s2 = fma2(g, xh, s2);
+          acc_g[i][j] = fma2(dv[j], xh, acc_g[i][j]);
+          acc_b[i][j] = add2(acc_b[i][j], dv[j]);
         }
       }
     }
-    s1 = warp_sum(s1) * inv_d;
-    s2 = warp_sum(s2) * inv_d;
+    if (dres) {   // issued ahead of the reductions; consumed in the output pass
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int vi = lane + 32 * i;
+        if (FULL || vi < nvec) rp[i] = __ldg(rr + vi);
+      }
+    }
+    float m1 = s1.x + s1.y, m2 = s2.x + s2.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    }
+    // dx = rstd*g - rstd*m1 - xhat*(rstd*m2)
+    const float2 c1 = splat2(-rstd * m1 * inv_d), c2 = splat2(-rstd * m2 * inv_d);
     uint4* dxr = reinterpret_cast<uint4*>(dx + row * D);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + 32 * i;
-      if (vi < nvec) {
-        float xv[8], dv[8], o[8];
-        unpack8(xp[i], xv);
-        unpack8(dp[i], dv);
-        const float4 g0 = *reinterpret_cast<const float4*>(sgam + vi * 8);
-        const float4 g1 = *reinterpret_cast<const float4*>(sgam + vi * 8 + 4);
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      if (FULL || vi < nvec) {
+        float2 xv[4], dv[4], gm[4], o[4];
+        unpack8p(xp[i], xv);
+        unpack8p(dp[i], dv);
+        load_param(g_lo, g_hi, vi, gm);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[j] - mean) * rstd;
-          o[j] = rstd * (dv[j] * gm[j] - s1 - xh * s2);
+        for (int j = 0; j < 4; ++j) {
+          const float2 xh = fma2(xv[j], r2, nmr);
+          const float2 g = mul2(dv[j], gm[j]);
+          o[j] = fma2(xh, c2, fma2(g, r2, c1));
         }
         if (dres) {
-          float r[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(dres + row * D) + vi), r);
+          float2 r[4];
+          unpack8p(rp[i], r);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
+          for (int j = 0; j < 4; ++j) o[j] = add2(o[j], r[j]);
         }
-        dxr[vi] = pack8(o);
+        dxr[vi] = pack8p(o);
       }
     }
   }
@@ -197,11 +290,11 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int vi = lane + 32 * i;
-    if (vi < nvec) {
+    if (FULL || vi < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        my_g[vi * 8 + j] = acc_g[i][j];
-        my_b[vi * 8 + j] = acc_b[i][j];
+      for (int j = 0; j < 4; ++j) {
+        *reinterpret_cast<float2*>(my_g + vi * 8 + 2 * j) = acc_g[i][j];
+        *reinterpret_cast<float2*>(my_b + vi * 8 + 2 * j) = acc_b[i][j];
       }
     }
   }
@@ -209,7 +302,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float sg = 0.f, sb = 0.f;
 #pragma unroll
-    for (int w = 0; w < kLnWarps; ++w) {
+    for (int w = 0; w < kLnBwdWarps; ++w) {
       sg += scratch[(size_t)w * 2 * D + c];
       sb += scratch[(size_t)w * 2 * D + D + c];
     }
@@ -252,12 +345,18 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* __restr
 template <int VPL>
 static int launch_ln_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,
                          float* rstd, long long rows, int D, float eps, cudaStream_t s) {
-  long long blocks = (rows + kLnWarps - 1) / kLnWarps;
-  const long long cap = (long long)num_sms() * 16;
+  long long blocks = ((rows + 1) / 2 + kLnWarps - 1) / kLnWarps;   // one warp per pair of rows
+  const long long cap = (long long)num_sms() * 2;                   // persistent: 2 resident blocks per SM
   if (blocks > cap) blocks = cap;
-  ln_fwd_kernel<VPL><<<(unsigned)blocks, kLnWarps * 32, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const float*>(gamma),
-      static_cast<const float*>(beta), static_cast<__nv_bfloat16*>(y), mean, rstd, rows, D, eps);
+  const size_t smem = (size_t)2 * D * sizeof(float);
+  if (D == 256 * VPL)
+    ln_fwd_kernel<VPL, true><<<(unsigned)blocks, kLnWarps * 32, smem, s>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const float*>(gamma),
+        static_cast<const float*>(beta), static_cast<__nv_bfloat16*>(y), mean, rstd, rows, D, eps);
+  else
+    ln_fwd_kernel<VPL, false><<<(unsigned)blocks, kLnWarps * 32, smem, s>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const float*>(gamma),
+        static_cast<const float*>(beta), static_cast<__nv_bfloat16*>(y), mean, rstd, rows, D, eps);
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CLIPA_OK;
@@ -267,14 +366,14 @@ template <int VPL>
 static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
                          const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
                          long long rows, int D, cudaStream_t s) {
-  long long blocks = (rows + kLnWarps - 1) / kLnWarps;
-  const long long cap = (long long)num_sms() * 2;
+  long long blocks = (rows + kLnBwdWarps - 1) / kLnBwdWarps;
+  const long long cap = (long long)num_sms();
   if (blocks > cap) blocks = cap;
-  const size_t smem = ((size_t)kLnWarps * 2 + 1) * D * sizeof(float);
-  auto kern = ln_bwd_kernel<VPL>;
+  const size_t smem = ((size_t)kLnBwdWarps * 2 + 1) * D * sizeof(float);
+  auto kern = (D == 256 * VPL) ? ln_bwd_kernel<VPL, true> : ln_bwd_kernel<VPL, false>;
   if (smem > 48 * 1024)
     CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)blocks, kLnWarps * 32, smem, s>>>(
+  kern<<<(unsigned)blocks, kLnBwdWarps * 32, smem, s>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
       static_cast<const float*>(gamma), mean, rstd, static_cast<const __nv_bfloat16*>(dres),
       static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, D);
