@@ -31,10 +31,10 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   int dev = 0;
   CLIPA_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal2));
+    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Smem<EPI>::kTotal));
     attr_set[dev] = true;
   }
-  kern<<<grid, kGemmThreads, kSmemTotal2, stream>>>(ta, tb, tc, tx, p);
+  kern<<<grid, kGemmThreads, Tc2Smem<EPI>::kTotal, stream>>>(ta, tb, tc, tx, p);
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CLIPA_OK;
@@ -50,7 +50,7 @@ static int encode_out_maps(GemmParams& p, int epi, const CUtensorMap& ta, CUtens
   if (!bf16_out) return CLIPA_OK;
   int rc = encode_tmap_2d_bf16(tc, p.C, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc * 2, 32, 32, 64);
   if (rc) return rc;
-  if (epi == EPI_BIAS_ACT && p.aux) {
+  if ((epi == EPI_BIAS_ACT || epi == EPI_DACT) && p.aux) {   // aux: TMA-stored (BIAS_ACT) / TMA-loaded (DACT, 2-CTA)
     rc = encode_tmap_2d_bf16(tx, p.aux, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldaux * 2, 32, 32, 64);
     if (rc) return rc;
   }

@@ -17,15 +17,37 @@
 namespace clipa {
 
 constexpr int kBN2 = 256;          // pair tile N
-constexpr int kStages2 = 6;
 constexpr int kABytes2 = kBM * kBK * 2;        // 128 x 64 bf16
 constexpr int kBBytes2 = (kBN2 / 2) * kBK * 2; // this CTA's half of B
 constexpr int kStageBytes2 = kABytes2 + kBBytes2;
-constexpr int kBarOffset2 = kStages2 * kStageBytes2;
-constexpr int kBiasOffset2 = kBarOffset2 + 256;
-constexpr int kStoreOffset2 = ((kBiasOffset2 + 2048 + 1023) / 1024) * 1024;   // 8 warps x 2 KB staging
-constexpr int kSmemTotal2 = kStoreOffset2 + kNumEpiWarps * 2048 + 1024;
-static_assert(kSmemTotal2 <= 227 * 1024, "2-CTA GEMM shared memory budget");
+
+// The DACT epilogue (dgrad of c_proj fused with gelu') streams a second M x N operand -- the saved
+// pre-activation -- through the epilogue.  Read with per-lane LDGs (one row per lane, 64 bytes per
+// chunk) every warp-level load touches 32 cache lines and the LSU/L1 path, not the tensor pipe,
+// paces the kernel (1130 vs 1475 TFLOP/s for the plain dgrad).  Here each epilogue warp fetches its
+// 32 x 32 chunk with one TMA load into a private 64B-swizzled buffer, kDactSideBufs chunks ahead.
+#ifndef CLIPA_DACT_STAGES
+#define CLIPA_DACT_STAGES 6
+#endif
+#ifndef CLIPA_DACT_SIDE_BUFS
+#define CLIPA_DACT_SIDE_BUFS 1
+#endif
+
+// Shared-memory layout of the 2-CTA kernel per epilogue type:
+//   [ A/B ring | barriers (512 B) | bias staging (2 x 256 fp32; none for DACT) | per-warp buffers ]
+// per-warp buffers: one 2 KB output staging tile (TMA store) + the DACT side-operand tiles.
+template <int EPI>
+struct Tc2Smem {
+  static constexpr int kStages = (EPI == EPI_DACT) ? CLIPA_DACT_STAGES : 6;
+  static constexpr int kSideBufs = (EPI == EPI_DACT) ? CLIPA_DACT_SIDE_BUFS : 0;
+  static constexpr int kBarOffset = kStages * kStageBytes2;
+  static constexpr int kBiasOffset = kBarOffset + 512;
+  static constexpr int kBiasBytes = (EPI == EPI_DACT) ? 0 : 2048;
+  static constexpr int kStoreOffset = ((kBiasOffset + kBiasBytes + 1023) / 1024) * 1024;
+  static constexpr int kWarpBytes = 2048 * (1 + kSideBufs);
+  static constexpr int kTotal = kStoreOffset + kNumEpiWarps * kWarpBytes + 1024;
+  static_assert(kTotal <= 227 * 1024, "2-CTA GEMM shared memory budget");
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -90,11 +112,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOffset2);   // used in the leader
+  using S = Tc2Smem<EPI>;
+  constexpr int kStages2 = S::kStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);   // used in the leader
   uint64_t* empty_bar = full_bar + kStages2;                              // per CTA
   uint64_t* tmem_full = empty_bar + kStages2;                             // per CTA
   uint64_t* tmem_empty = tmem_full + 2;                                   // used in the leader
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* side_bar = tmem_empty + 2;                                    // [8 warps][kSideBufs], DACT only
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(side_bar + kNumEpiWarps * 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,6 +136,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * kNumEpiWarps);  // epilogue warps of both CTAs
+    }
+    if constexpr (EPI == EPI_DACT) {
+      tma_prefetch_desc(&tmap_aux);
+      for (int i = 0; i < kNumEpiWarps * 2; ++i) mbar_init(&side_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -204,6 +233,80 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     constexpr int kColsPerWarp = kBN2 / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if constexpr (EPI == EPI_DACT) {
+      // ---- dgrad x gelu'(saved pre-activation): side operand through per-warp TMA loads
+      constexpr int NB = S::kSideBufs;
+      uint8_t* sbuf = smem + S::kStoreOffset + ew * S::kWarpBytes;   // output staging (TMA store)
+      uint8_t* lbuf = sbuf + 2048;                                   // NB side-operand tiles
+      uint64_t* sbar = side_bar + ew * 2;
+      const int sw = (lane >> 1) & 3;
+      // global chunk counter g: tile = g / 4 of this cluster's tile sequence, 32-column chunk = g % 4
+      auto issue_side = [&](int g) {
+        const int w = cluster_id + (g >> 2) * num_clusters;
+        if (w < p.num_items && lane == 0) {
+          const int m_blk = w / p.n_blocks;
+          const int n_blk = w - m_blk * p.n_blocks;
+          uint64_t* b = &sbar[g % NB];
+          mbar_expect_tx(b, 2048);
+          tma_load_2d(lbuf + (g % NB) * 2048, &tmap_aux, b, n_blk * kBN2 + half * kColsPerWarp + (g & 3) * 32,
+                      m_blk * (2 * kBM) + (int)rank * kBM + q * 32);
+        }
+      };
+#pragma unroll
+      for (int g0 = 0; g0 < NB; ++g0) issue_side(g0);
+      int g = 0;
+      for (int w = cluster_id; w < p.num_items; w += num_clusters) {
+        const int m_blk = w / p.n_blocks;
+        const int n_blk = w - m_blk * p.n_blocks;
+        const int row0_warp = m_blk * (2 * kBM) + (int)rank * kBM + q * 32;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_warp = tmem_base + acc * kBN2 + half * kColsPerWarp + (static_cast<uint32_t>(q * 32) << 16);
+        uint32_t vnext[32];
+        tmem_ld_32x32(t_warp, vnext);
+#pragma unroll 1
+        for (int c = 0; c < kColsPerWarp / 32; ++c, ++g) {
+          const int col0 = n_blk * kBN2 + half * kColsPerWarp + c * 32;
+          float f[32];
+          tmem_ld_wait_regs(vnext);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vnext[j]);
+          if (c + 1 < kColsPerWarp / 32) {
+            tmem_ld_32x32(t_warp + (c + 1) * 32, vnext);
+          } else {   // accumulator stage drained: hand it back before the math of the last chunk
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_addr(smem_u32(&tmem_empty[acc])));
+          }
+          mbar_wait(&sbar[g % NB], (g / NB) & 1);
+          uint4 side[4];
+          const uint8_t* lrow = lbuf + (g % NB) * 2048 + lane * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) side[k] = *reinterpret_cast<const uint4*>(lrow + ((k ^ sw) << 4));
+          __syncwarp();
+          issue_side(g + NB);   // the tile just read is free again
+          if (col0 >= p.N) continue;  // warp-uniform
+          float a[32];
+          unpack_bf16x32(side, a);   // rows >= M / columns >= N arrive as zeros and are clipped by the store
+          if (p.act == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float2 r = mul2(make_float2(f[j], f[j + 1]), gelu_erf_bwd2(make_float2(a[j], a[j + 1])));
+              f[j] = r.x;
+              f[j + 1] = r.y;
+            }
+          } else if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 1);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= act_bwd(a[j], 2);
+          }
+          chunk_store_tma(&tmap_c, sbuf, f, col0, row0_warp);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else {
     for (int w = cluster_id; w < p.num_items; w += num_clusters) {
       const int split = w / items_mn;
       const int r = w - split * items_mn;
@@ -211,18 +314,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int n_blk = r - m_blk * p.n_blocks;
       const long long row = (long long)m_blk * (2 * kBM) + (long long)rank * kBM + q * 32 + lane;
       const bool row_ok = row < p.M;
-      float* sbias_tile = reinterpret_cast<float*>(smem + kBiasOffset2) + acc * 256;
+      float* sbias_tile = reinterpret_cast<float*>(smem + S::kBiasOffset) + acc * 256;
       epi_stage_bias(p, sbias_tile, n_blk * kBN2, kBN2);   // overlaps the MMAs of this tile
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_warp = tmem_base + acc * kBN2 + half * kColsPerWarp + (static_cast<uint32_t>(q * 32) << 16);
       epi_run_store<EPI>(p, t_warp, row, row_ok, n_blk * kBN2, half * kColsPerWarp, kColsPerWarp, sbias_tile,
-                         &tmap_c, &tmap_aux, smem + kStoreOffset2 + ew * 2048, [&]() {
+                         &tmap_c, &tmap_aux, smem + S::kStoreOffset + ew * S::kWarpBytes, [&]() {
                            tc_fence_before();
                            __syncwarp();
                            if (lane == 0) mbar_arrive_cluster(leader_addr(smem_u32(&tmem_empty[acc])));
                          });
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
     }
   }
 
