@@ -2,8 +2,9 @@
 // query of a (sample, head) problem; configs 1, 2, 3, 5 and every text tower).  The mma.sync kernels
 // in attention.cu cover longer sequences and other head widths.
 //
-// FORWARD -- persistent CTA, 10 warps, two problems in flight:
-//   warp 0      TMA producer: Q, K, V head slices (L rows x 128 B, 128B-swizzled) -> 2-stage smem ring
+// FORWARD -- persistent CTA, 10 warps, two problems in flight (S of problem i+2 is issued as soon as
+// the softmax of problem i has left TMEM, so a softmax group never waits for its scores):
+//   warp 0      TMA producer: Q, K, V head slices (L rows x 128 B, 128B-swizzled) -> 3-stage smem ring
 //   warp 1      MMA issuer:   S = Q K^T  (tcgen05.mma M128 x N=ceil16(L) x K64, fp32 in TMEM)
 //                             O = P V    (A = P from smem, B = V consumed MN-major in place)
 //   warps 2-5   softmax/epilogue group for even problems   } one thread per query row:
@@ -29,8 +30,11 @@ constexpr int kTcThreads = 320;
 constexpr int kTcTileBytes = 128 * 128;                     // 128 rows x 128 B
 constexpr int kTcStageBytes = 3 * kTcTileBytes;             // Q, K, V
 constexpr int kTcPBytes = 2 * kTcTileBytes;                 // P: 128 rows x 128 keys bf16 = 2 swizzle atoms
-constexpr int kTcSmemBar = 2 * kTcStageBytes + 2 * kTcPBytes;
-constexpr int kTcSmemTotal = kTcSmemBar + 256 + 1024;
+// Q/K/V smem ring: 3 slots for one-sample tiles, 2 for packed tiles (which then keep 63 KB of L1 for
+// their all-rows-active output stores; with the 3-slot footprint they ran 10 % slower)
+constexpr int tc_ring(bool packed) { return packed ? 2 : 3; }
+constexpr int tc_smem_bar(bool packed) { return tc_ring(packed) * kTcStageBytes + 2 * kTcPBytes; }
+constexpr int tc_smem_total(bool packed) { return tc_smem_bar(packed) + 256 + 1024; }
 
 struct AttnTcParams {
   __nv_bfloat16* out;
@@ -92,15 +96,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* p_base = smem + 2 * kTcStageBytes;
+  constexpr int kRing = tc_ring(PACKED);
+  constexpr int kTcSmemBar = tc_smem_bar(PACKED);
+  uint8_t* p_base = smem + kRing * kTcStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcSmemBar);
-  uint64_t* full = bars;           // [2] TMA landed
-  uint64_t* kv_empty = bars + 2;   // [2] smem stage free
-  uint64_t* s_full = bars + 4;     // [2] S in TMEM
-  uint64_t* p_full = bars + 6;     // [2] P in smem
-  uint64_t* o_full = bars + 8;     // [2] O in TMEM
-  uint64_t* t_free = bars + 10;    // [2] TMEM stage + P buffer free
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* full = bars;           // [3] TMA landed
+  uint64_t* kv_empty = bars + 3;   // [3] smem stage free
+  uint64_t* s_full = bars + 6;     // [2] S in TMEM
+  uint64_t* p_full = bars + 8;     // [2] P in smem (and S consumed)
+  uint64_t* o_full = bars + 10;    // [2] O in TMEM
+  uint64_t* t_free = bars + 12;    // [2] TMEM stage + P buffer free (PACKED schedule only)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  // Two schedules, chosen by measurement (profiles/r01_attn_fwd_schedules.log):
+  //  * one sample per tile (ViT towers): 3-slot operand ring, S(i+2) is issued right behind PV(i) --
+  //    the group finds its next scores in TMEM when it comes back from storing O(i)
+  //    (L = 82: 222 -> 148 us);
+  //  * packed tiles (text towers, 48 KB of operands per tile, HBM-latency-bound): 2-slot ring, S(i)
+  //    issued once the group has read O(i-2); the eager schedule was 10-25 % slower here.
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L, H = p.H, D = H * kTcHd;
@@ -114,9 +126,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
   fence_proxy_async_smem();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kRing; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
@@ -136,8 +150,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < n_local; ++i) {
-        const int s = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
+        const int s = i % kRing;
+        const uint32_t ph = (i / kRing) & 1;
         const int prob = blockIdx.x + i * gridDim.x;
         const int n = (prob / H) * p.G, h = prob % H;   // first sample of the tile, head
         mbar_wait(&kv_empty[s], ph ^ 1);
@@ -153,13 +167,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
       const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.npad, false, false);
       const uint32_t idesc_o = make_idesc_bf16(128, kTcHd, false, true);
       const int ksteps = p.npad / 16;
-      auto issue_pv = [&](int j) {
-        const int sj = j & 1;
-        const uint32_t phj = (j >> 1) & 1;
-        mbar_wait(&p_full[sj], phj);
+      // TMEM stage / P buffer j & 1, smem ring slot j % kRing
+      auto issue_s = [&](int j) {
+        const int r = j % kRing;
+        mbar_wait(&full[r], (j / kRing) & 1);
+        if constexpr (PACKED) mbar_wait(&t_free[j & 1], ((j >> 1) & 1) ^ 1);   // group has read O(j-2)
+        tc_fence_after();
+        const uint32_t qa = smem_u32(smem + r * kTcStageBytes);
+        const uint32_t ka = qa + kTcTileBytes;
+        const uint32_t d_s = tmem_base + (j & 1) * 256;
+#pragma unroll
+        for (int k = 0; k < kTcHd / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(qa + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(ka + k * 32, 16, 1024);
+          umma_bf16(d_s, da, db, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[j & 1]);
+      };
+      auto issue_pv = [&](int i) {
+        const int sj = i & 1;
+        const int r = i % kRing;
+        // P(i) written, S(i) consumed; the O columns of this TMEM stage were read out before the
+        // group started on problem i, and P is not rewritten until the group has seen o_full(i)
+        mbar_wait(&p_full[sj], (i >> 1) & 1);
         tc_fence_after();
         const uint32_t pa = smem_u32(p_base + sj * kTcPBytes);
-        const uint32_t va = smem_u32(smem + sj * kTcStageBytes + 2 * kTcTileBytes);
+        const uint32_t va = smem_u32(smem + r * kTcStageBytes + 2 * kTcTileBytes);
         const uint32_t d_o = tmem_base + sj * 256 + 128;
         for (int kk = 0; kk < ksteps; ++kk) {
           const uint64_t da = make_smem_desc_sw128(pa + (kk >> 2) * kTcTileBytes + (kk & 3) * 32, 16, 1024);
@@ -167,27 +200,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
           umma_bf16(d_o, da, db, idesc_o, kk > 0 ? 1u : 0u);
         }
         umma_commit(&o_full[sj]);
-        umma_commit(&kv_empty[sj]);
+        umma_commit(&kv_empty[r]);
       };
-      for (int i = 0; i < n_local; ++i) {
-        const int s = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
-        mbar_wait(&full[s], ph);
-        mbar_wait(&t_free[s], ph ^ 1);
-        tc_fence_after();
-        const uint32_t qa = smem_u32(smem + s * kTcStageBytes);
-        const uint32_t ka = qa + kTcTileBytes;
-        const uint32_t d_s = tmem_base + s * 256;
-#pragma unroll
-        for (int k = 0; k < kTcHd / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(qa + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(ka + k * 32, 16, 1024);
-          umma_bf16(d_s, da, db, idesc_s, k > 0 ? 1u : 0u);
+      if constexpr (PACKED) {
+        for (int i = 0; i < n_local; ++i) {
+          issue_s(i);
+          if (i > 0) issue_pv(i - 1);
         }
-        umma_commit(&s_full[s]);
-        if (i > 0) issue_pv(i - 1);
+        if (n_local > 0) issue_pv(n_local - 1);
+      } else {
+        if (n_local > 0) issue_s(0);
+        if (n_local > 1) issue_s(1);
+        for (int i = 0; i < n_local; ++i) {
+          issue_pv(i);
+          if (i + 2 < n_local) issue_s(i + 2);   // scores of the group's next problem, behind PV(i)
+        }
       }
-      if (n_local > 0) issue_pv(n_local - 1);
     }
   } else {
     const int grp = (warp - 2) >> 2;  // 0: even problems, 1: odd problems
@@ -263,9 +291,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         tmem_ld_32x32(t_o, o0);
         tmem_ld_32x32(t_o + 32, o1);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_free[grp]);
+        if constexpr (PACKED) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_free[grp]);
+        }
         if (row_valid) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)n * L + row) * D + h * kTcHd);
           float f[32];
@@ -279,7 +309,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
           for (int g8 = 0; g8 < 4; ++g8) dst[4 + g8] = pack8_bf16(f + 8 * g8);
           p.lse[((long long)(n + span.sample) * H + h) * L + span.token] = (ms + log2f(l)) * 0.69314718055994531f;
         }
-      } else {
+      } else if constexpr (PACKED) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_free[grp]);
@@ -318,9 +348,10 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, i
   int grid = num_sms();
   if (grid > total) grid = (int)total;
   const int nch = (p.npad + 31) / 32;
+  const int smem_bytes = tc_smem_total(G > 1);
   auto launch = [&](auto kern) -> int {
-    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemTotal));
-    kern<<<grid, kTcThreads, kTcSmemTotal, stream>>>(tm, p);
+    CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    kern<<<grid, kTcThreads, smem_bytes, stream>>>(tm, p);
     return CLIPA_OK;
   };
   auto pick = [&](auto causal_c, auto packed_c) -> int {
