@@ -1,10 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-mkdir -p gpurun_out/attnf2
+mkdir -p gpurun_out/n8
 export PYTHONPATH="$PWD:$PYTHONPATH"
-timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k attention > gpurun_out/attnf2/pytest_attn.log 2>&1
-echo "pytest attn exit=$?"; tail -n 3 gpurun_out/attnf2/pytest_attn.log
-for v in new prev new prev; do
-  if [ $v = prev ]; then export CLIPA_B200_LIB=$PWD/clipa_b200/lib/libclipa_b200_prev.so; else unset CLIPA_B200_LIB; fi
-  echo "--- $v"; timeout 300 python tools/prof_attn_text.py 2>&1 | grep -E "PERF|Error|error" | tee -a gpurun_out/attnf2/perf_$v.log
-done
+nvidia-smi --query-gpu=index,name,clocks.sm,power.draw --format=csv > gpurun_out/n8/gpu.txt 2>&1
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 6 --warmup 3 > gpurun_out/n8/bench_8gpu.json 2> gpurun_out/n8/bench_8gpu.err
+echo "bench8 exit=$?"; tail -c 2500 gpurun_out/n8/bench_8gpu.json; tail -n 5 gpurun_out/n8/bench_8gpu.err
