@@ -320,7 +320,7 @@ def main():
                        "image_px": wl["image"], "image_tokens_incl_cls": model.visual.positional_embedding.shape[0],
                        "text_tokens": ctx, "global_batch": gb, "per_gpu_batch": bl,
                        "micro_batch": min(bl, args.micro_batch),
-                       "schedule": "plain fwd/bwd" if bl <= args.micro_batch else "GradCache (extra no-grad forward)",
+                       "schedule": "plain fwd/bwd" if bl <= args.micro_batch else "GradCache (N chunks: N-1 no-grad forwards + N fwd/bwd; last chunk keeps its graph)",
                        "parallelism": f"dp{world}", "precision": args.precision,
                        "optimizer": "AdamW (clipa_adamw_step: fused update + bf16 shadow + grad clear) inside the timed step", "l2": "inputs_exceed_L2",
                        "loss_last": float(last_loss),

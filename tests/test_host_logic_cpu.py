@@ -95,3 +95,50 @@ def test_create_loss_signature():
                            world_size=8, horovod=False)
     loss = open_clip.create_loss(args)
     assert isinstance(loss, open_clip.ClipLoss) and loss.rank == 3 and loss.world_size == 8 and loss.local_loss
+
+
+def test_gradcache_schedule_matches_single_pass_cpu():
+    """TrainStep.forward_backward's chunked (GradCache, train.py:216-256) schedule -- including the kept graph
+    of the last chunk and a ragged tail -- accumulates the same gradients as one pass.  Pure host logic: a small
+    torch stand-in model and a torch contrastive loss replace the CUDA path."""
+    import torch
+    import torch.nn.functional as F
+    from clipa_b200.training import TrainStep
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.vis = torch.nn.Linear(3 * 4 * 4, 8)
+            self.txt = torch.nn.Embedding(11, 8)
+            self.logit_scale = torch.nn.Parameter(torch.tensor(2.0))
+            self.visual = self.vis
+            self.calls = 0
+
+        def forward(self, images, texts):
+            self.calls += 1
+            i = F.normalize(self.vis(images.float().flatten(1)), dim=-1)
+            t = F.normalize(self.txt(texts).mean(1), dim=-1)
+            return i, t, self.logit_scale.exp()
+
+    def loss_fn(i, t, scale):
+        logits = scale * i @ t.t()
+        labels = torch.arange(i.shape[0])
+        return (F.cross_entropy(logits, labels) + F.cross_entropy(logits.t(), labels)) / 2
+
+    torch.manual_seed(1)
+    images = torch.randn(10, 3, 4, 4)
+    texts = torch.randint(0, 11, (10, 5))
+    grads = []
+    for mb in (10, 4, 3):
+        model = Toy()
+        ts = TrainStep(model, micro_batch=mb, image_mean=(0., 0., 0.), image_std=(1., 1., 1.))
+        ts.loss_fn = loss_fn
+        loss = ts.forward_backward(images, texts)
+        n_chunks = -(-10 // mb)
+        assert model.calls == (1 if n_chunks == 1 else 2 * n_chunks - 1)
+        grads.append((loss.item(), [p.grad.clone() for p in ts.params]))
+    for l, g in grads[1:]:
+        assert abs(l - grads[0][0]) < 1e-6
+        for a, b in zip(g, grads[0][1]):
+            assert torch.allclose(a, b, atol=1e-6, rtol=1e-5)
