@@ -311,6 +311,12 @@ def main():
     if rank == 0:
         pk, pk_src = peaks()
         peak = pk["bf16_tflops_sustained"]
+        # dram__bytes_read.sum + dram__bytes_write.sum of the largest-share GEMM launch, from the committed
+        # ncu --set full capture (profiles/ncu_traffic.json names the capture); absent -> null
+        try:
+            traffic = json.loads((Path(__file__).resolve().parent / "profiles" / "ncu_traffic.json").read_text())
+        except (OSError, ValueError):
+            traffic = {}
         per_gpu_pairs = value / world
         out = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -329,9 +335,10 @@ def main():
                        "algorithmic_gflop_per_pair": wl["gflop_per_pair"],
                        "model_flops_utilization": per_gpu_pairs * wl["gflop_per_pair"] / (peak * 1e3)},
             "clocks": clocks, "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all epilogues/majors)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05, all epilogues/majors)",
                          "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
-                         "traffic": None, "peak_source": pk_src + ", sustained figure (kernel timed inside a long step)",
+                         "traffic": traffic.get("dram_bytes_per_launch"), "traffic_of": traffic.get("of"),
+                         "peak_source": pk_src + ", sustained figure (kernel timed inside a long step)",
                          "gemm_launches_timed": gemm_calls, "gemm_ms_per_step": gemm_ms / args.steps,
                          "gemm_share_of_step": gemm_ms / args.steps / ms_step},
         }

@@ -49,17 +49,48 @@ def _bias(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return p.detach() if p.dtype in (_BF16, torch.float32) else p.detach().float()
 
 
-def _wgrad(dy: torch.Tensor, x: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
-    """dW[out,in] = dy[M,out]^T @ x[M,in]: both operands consumed MN-major, split-K, fp32 atomics."""
-    dw = torch.zeros(dy.shape[1], x.shape[1], dtype=torch.float32, device=dy.device)
+def grad_sink(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The fp32 `.grad` buffer of a parameter that opted into direct accumulation (TrainStep sets
+    `p._clipa_direct_grad` on parameters whose `.grad` is a view of its flat, pre-zeroed gradient
+    buffer).  Every gradient kernel of this library ACCUMULATES (split-K `red.add`, atomics), so it can
+    write there directly and the autograd node returns None for that input: no zero-fill of a
+    temporary and no AccumulateGrad add per parameter (~900 tiny launches and ~5 GB per ViT-L/14 step)."""
+    if p is None or not getattr(p, "_clipa_direct_grad", False):
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+        return None
+    return g
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, like: torch.Tensor, direct: bool = True) -> Optional[torch.Tensor]:
+    """dW[out,in] = dy[M,out]^T @ x[M,in]: both operands consumed MN-major, split-K, fp32 atomics.
+    Returns None when the result was accumulated straight into `like.grad` (see grad_sink)."""
+    sink = grad_sink(like) if direct else None
+    dw = sink if sink is not None else torch.zeros(dy.shape[1], x.shape[1], dtype=torch.float32, device=dy.device)
     ops.gemm(dy.t(), x.t(), dw, epilogue=EPI_ATOMIC_F32, split_k=-1)
+    if sink is not None:
+        return None
     return dw if like.dtype == torch.float32 else dw.to(like.dtype)
 
 
-def _bgrad(dy: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
-    db = torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
+def _bgrad(dy: torch.Tensor, like: torch.Tensor) -> Optional[torch.Tensor]:
+    sink = grad_sink(like)
+    db = sink if sink is not None else torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
     ops.colsum_accum(dy, db)
+    if sink is not None:
+        return None
     return db if like.dtype == torch.float32 else db.to(like.dtype)
+
+
+def _ln_grad_bufs(weight: torch.Tensor, bias: torch.Tensor):
+    """(dgamma, dbeta, direct): accumulation targets for layernorm_bwd."""
+    sg, sb = grad_sink(weight), grad_sink(bias)
+    if sg is not None and sb is not None:
+        return sg, sb, True
+    D = weight.shape[0]
+    return (torch.zeros(D, dtype=torch.float32, device=weight.device),
+            torch.zeros(D, dtype=torch.float32, device=weight.device), False)
 
 
 class LinearFn(torch.autograd.Function):
@@ -87,7 +118,7 @@ class LinearFn(torch.autograd.Function):
             dx = torch.empty_like(x)
             ops.gemm(dy, wb.t(), dx)               # dx[M,in] = dy[M,out] @ W[out,in]
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(dy, x, weight)             # [out, in]
+            dw = _wgrad(dy, x, weight, direct=not ctx.transposed)   # [out, in]
             if ctx.transposed:
                 dw = dw.t().contiguous()
         if bias is not None and ctx.needs_input_grad[2]:
@@ -105,10 +136,10 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight, bias, mean, rstd = ctx.saved_tensors
-        D = x.shape[-1]
-        dg = torch.zeros(D, dtype=torch.float32, device=x.device)
-        db = torch.zeros(D, dtype=torch.float32, device=x.device)
+        dg, db, direct = _ln_grad_bufs(weight, bias)
         dx = ops.layernorm_bwd(dy.contiguous(), x, _f32(weight), mean, rstd, None, dg, db)
+        if direct:
+            return dx, None, None, None
         return dx, dg.to(weight.dtype), db.to(bias.dtype), None
 
 
@@ -175,8 +206,7 @@ class ResidualBlockFn(torch.autograd.Function):
         dh2 = torch.empty(M, D, dtype=_BF16, device=dev)
         ops.gemm(df, compute_copy(w_fc).t(), dh2)
         del df
-        d_ln2_w = torch.zeros(D, dtype=torch.float32, device=dev)
-        d_ln2_b = torch.zeros(D, dtype=torch.float32, device=dev)
+        d_ln2_w, d_ln2_b, direct2 = _ln_grad_bufs(ln2_w, ln2_b)
         dx1 = ops.layernorm_bwd(dh2, x1, _f32(ln2_w), mean2, rstd2, dy, d_ln2_w, d_ln2_b)
         del dh2
         # ---- attention
@@ -194,11 +224,12 @@ class ResidualBlockFn(torch.autograd.Function):
         dh1 = torch.empty(M, D, dtype=_BF16, device=dev)
         ops.gemm(dqkv, compute_copy(w_in).t(), dh1)
         del dqkv
-        d_ln1_w = torch.zeros(D, dtype=torch.float32, device=dev)
-        d_ln1_b = torch.zeros(D, dtype=torch.float32, device=dev)
+        d_ln1_w, d_ln1_b, direct1 = _ln_grad_bufs(ln1_w, ln1_b)
         dx = ops.layernorm_bwd(dh1, x, _f32(ln1_w), mean1, rstd1, dx1, d_ln1_w, d_ln1_b)
-        return (dx, d_ln1_w.to(ln1_w.dtype), d_ln1_b.to(ln1_b.dtype), d_w_in, d_b_in, d_w_out, d_b_out,
-                d_ln2_w.to(ln2_w.dtype), d_ln2_b.to(ln2_b.dtype), d_w_fc, d_b_fc, d_w_proj, d_b_proj,
+        g_ln1 = (None, None) if direct1 else (d_ln1_w.to(ln1_w.dtype), d_ln1_b.to(ln1_b.dtype))
+        g_ln2 = (None, None) if direct2 else (d_ln2_w.to(ln2_w.dtype), d_ln2_b.to(ln2_b.dtype))
+        return (dx, g_ln1[0], g_ln1[1], d_w_in, d_b_in, d_w_out, d_b_out,
+                g_ln2[0], g_ln2[1], d_w_fc, d_b_fc, d_w_proj, d_b_proj,
                 None, None, None, None, None, None)
 
 

@@ -79,6 +79,7 @@ class TrainStep:
                     fp[off:off + n].copy_(p.data.reshape(-1))
                     p.data = fp[off:off + n].view_as(p)
                     p.grad = fg[off:off + n].view_as(p)
+                    p._clipa_direct_grad = True   # gradient kernels accumulate straight into the flat buffer
                     shadow = fb[off:off + n].view_as(p)
                     shadow.copy_(p.data)
                     p._clipa_bf16 = (p._version, shadow)

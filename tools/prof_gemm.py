@@ -1,10 +1,11 @@
-"""Tiny driver for ncu: the four forward GEMM shapes of a ViT-L/14 block at 82 tokens x 1024 samples,
-one dgrad and one wgrad."""
+"""Tiny driver for ncu: the four forward GEMM shapes of a ViT-L/14 block at 82 tokens x SAMPLES samples
+(default 1024; `python tools/prof_gemm.py 4096` = the bench's per-GPU shard), one dgrad and one wgrad."""
+import sys
 import torch
 from clipa_b200 import ops
 from clipa_b200._lib import EPI_ATOMIC_F32, EPI_BIAS_ACT
 dev = torch.device("cuda:0")
-M, D = 82 * 1024, 1024
+M, D = 82 * (int(sys.argv[1]) if len(sys.argv) > 1 else 1024), 1024
 x = torch.randn(M, D, device=dev).bfloat16()
 x4 = torch.randn(M, 4 * D, device=dev).bfloat16()
 w_in = torch.randn(3 * D, D, device=dev).bfloat16()
