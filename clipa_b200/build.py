@@ -28,6 +28,12 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_flags() -> list:
+    """Extra nvcc flags for experiment builds, e.g. CLIPA_B200_NVCC_FLAGS="-DCLIPA_UNIFORM_ISSUE=1"
+    together with CLIPA_B200_LIB_NAME=libclipa_b200_uni.so (loaded through the CLIPA_B200_LIB variable)."""
+    return os.environ.get("CLIPA_B200_NVCC_FLAGS", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and Path(cand).exists():
@@ -37,7 +43,7 @@ def _nvcc() -> str:
 
 def _digest(src: Path) -> str:
     h = hashlib.sha256()
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     for f in sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [src, PKG.parent / "include" / "clipa_b200.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
@@ -45,8 +51,12 @@ def _digest(src: Path) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every csrc/*.cu and link the shared library. Incremental via content hashes."""
+    """Compile every csrc/*.cu and link the shared library. Incremental via content hashes.
+    Experiment builds (CLIPA_B200_LIB_NAME set) get their own object directory and library file."""
     nvcc = _nvcc()
+    name = os.environ.get("CLIPA_B200_LIB_NAME", "")
+    OBJDIR = PKG / "lib" / ("obj_" + Path(name).stem if name else "obj")
+    LIB = LIBDIR / name if name else LIBDIR / "libclipa_b200.so"
     OBJDIR.mkdir(parents=True, exist_ok=True)
     sources = sorted(CSRC.glob("*.cu"))
     jobs = []
@@ -60,7 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(job):
         src, obj, stamp, dig = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *_extra_flags(), "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -163,7 +163,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const IssueMode im = issue_mode(lane);
+    if (im.in_loop) {
       const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.npad, false, false);
       const uint32_t idesc_o = make_idesc_bf16(128, kTcHd, false, true);
       const int ksteps = p.npad / 16;
@@ -180,9 +181,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         for (int k = 0; k < kTcHd / 16; ++k) {
           const uint64_t da = make_smem_desc_sw128(qa + k * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(ka + k * 32, 16, 1024);
-          umma_bf16(d_s, da, db, idesc_s, k > 0 ? 1u : 0u);
+          if (im.issue) umma_bf16(d_s, da, db, idesc_s, k > 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[j & 1]);
+        if (im.issue) umma_commit(&s_full[j & 1]);
+        im.sync();
       };
       auto issue_pv = [&](int i) {
         const int sj = i & 1;
@@ -197,10 +199,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPar
         for (int kk = 0; kk < ksteps; ++kk) {
           const uint64_t da = make_smem_desc_sw128(pa + (kk >> 2) * kTcTileBytes + (kk & 3) * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(va + kk * 2048, 8192, 1024);
-          umma_bf16(d_o, da, db, idesc_o, kk > 0 ? 1u : 0u);
+          if (im.issue) umma_bf16(d_o, da, db, idesc_o, kk > 0 ? 1u : 0u);
         }
-        umma_commit(&o_full[sj]);
-        umma_commit(&kv_empty[r]);
+        if (im.issue) umma_commit(&o_full[sj]);
+        if (im.issue) umma_commit(&kv_empty[r]);
+        im.sync();
       };
       if constexpr (PACKED) {
         for (int i = 0; i < n_local; ++i) {
@@ -514,7 +517,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const IssueMode im = issue_mode(lane);
+    if (im.in_loop) {
       const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.npad, false, false);   // A K-major, B K-major
       const uint32_t idesc_t = make_idesc_bf16(128, kTcHd, true, true);                // A MN (P^T/dS^T), B MN
       const uint32_t idesc_q = make_idesc_bf16(128, kTcHd, false, true);               // A K (dS), B MN (K)
@@ -530,13 +534,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
         const uint32_t ka = qa + kTcTileBytes, va = qa + 2 * kTcTileBytes, doa = qa + 3 * kTcTileBytes;
 #pragma unroll
         for (int k = 0; k < kTcHd / 16; ++k)
-          umma_bf16(tmem_base + kColS, make_smem_desc_sw128(qa + k * 32, 16, 1024),
+          if (im.issue) umma_bf16(tmem_base + kColS, make_smem_desc_sw128(qa + k * 32, 16, 1024),
                     make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < kTcHd / 16; ++k)
-          umma_bf16(tmem_base + kColDp, make_smem_desc_sw128(doa + k * 32, 16, 1024),
+          if (im.issue) umma_bf16(tmem_base + kColDp, make_smem_desc_sw128(doa + k * 32, 16, 1024),
                     make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(sdp_full);
+        if (im.issue) umma_commit(sdp_full);
+        im.sync();
       };
       if (n_local > 0) issue_scores(0);
       for (int i = 0; i < n_local; ++i) {
@@ -555,17 +560,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           const uint64_t a_ds = make_smem_desc_sw128(dsa + kk * 2048, kTcTileBytes, 1024);
           const uint64_t b_do = make_smem_desc_sw128(doa + kk * 2048, 8192, 1024);
           const uint64_t b_q = make_smem_desc_sw128(qa + kk * 2048, 8192, 1024);
-          umma_bf16(tmem_base + kColDv, a_p, b_do, idesc_t, kk > 0 ? 1u : 0u);
-          umma_bf16(tmem_base + kColDk, a_ds, b_q, idesc_t, kk > 0 ? 1u : 0u);
+          if (im.issue) umma_bf16(tmem_base + kColDv, a_p, b_do, idesc_t, kk > 0 ? 1u : 0u);
+          if (im.issue) umma_bf16(tmem_base + kColDk, a_ds, b_q, idesc_t, kk > 0 ? 1u : 0u);
         }
         for (int kk = 0; kk < ksteps; ++kk) {
           // contraction over keys: A = dS K-major, B = K MN-major
           const uint64_t a_ds = make_smem_desc_sw128(dsa + (kk >> 2) * kTcTileBytes + (kk & 3) * 32, 16, 1024);
           const uint64_t b_k = make_smem_desc_sw128(ka + kk * 2048, 8192, 1024);
-          umma_bf16(tmem_base + kColDq, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
+          if (im.issue) umma_bf16(tmem_base + kColDq, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
         }
-        umma_commit(grad_full);
-        umma_commit(&kv_empty[s]);
+        if (im.issue) umma_commit(grad_full);
+        if (im.issue) umma_commit(&kv_empty[s]);
+        im.sync();
         if (i + 1 < n_local) issue_scores(i + 1);
       }
     }
@@ -776,7 +782,8 @@ attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const IssueMode im = issue_mode(lane);
+    if (im.in_loop) {
       const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.npad, false, false);   // A K-major, B K-major
       const uint32_t idesc_t = make_idesc_bf16(128, kTcHd, true, true);                // A MN (P^T/dS^T), B MN
       const uint32_t idesc_q = make_idesc_bf16(128, kTcHd, false, true);               // A K (dS), B MN (K)
@@ -789,13 +796,14 @@ attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         const uint32_t ka = qa + kPTile, va = qa + 2 * kPTile, doa = qa + 3 * kPTile;
 #pragma unroll
         for (int k = 0; k < kTcHd / 16; ++k)
-          umma_bf16(tmem_base + kColS, make_smem_desc_sw128(qa + k * 32, 16, 1024),
+          if (im.issue) umma_bf16(tmem_base + kColS, make_smem_desc_sw128(qa + k * 32, 16, 1024),
                     make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < kTcHd / 16; ++k)
-          umma_bf16(tmem_base + kColDp, make_smem_desc_sw128(doa + k * 32, 16, 1024),
+          if (im.issue) umma_bf16(tmem_base + kColDp, make_smem_desc_sw128(doa + k * 32, 16, 1024),
                     make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(sdp_full);
+        if (im.issue) umma_commit(sdp_full);
+        im.sync();
       };
       if (n_local > 0) issue_scores(0);
       for (int i = 0; i < n_local; ++i) {
@@ -815,17 +823,18 @@ attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           const uint64_t a_ds = make_smem_desc_sw128(dsa + kk * 2048, kPTile, 1024);
           const uint64_t b_do = make_smem_desc_sw128(doa + kk * 2048, 8192, 1024);
           const uint64_t b_q = make_smem_desc_sw128(qa + kk * 2048, 8192, 1024);
-          umma_bf16(tmem_base + kColDv, a_p, b_do, idesc_t, kk > 0 ? 1u : 0u);
-          umma_bf16(tmem_base + kColDk, a_ds, b_q, idesc_t, kk > 0 ? 1u : 0u);
+          if (im.issue) umma_bf16(tmem_base + kColDv, a_p, b_do, idesc_t, kk > 0 ? 1u : 0u);
+          if (im.issue) umma_bf16(tmem_base + kColDk, a_ds, b_q, idesc_t, kk > 0 ? 1u : 0u);
         }
         for (int kk = 0; kk < ksteps; ++kk) {
           // contraction over keys: A = dS K-major, B = K MN-major
           const uint64_t a_ds = make_smem_desc_sw128(dsa + (kk >> 2) * kPTile + (kk & 3) * 32, 16, 1024);
           const uint64_t b_k = make_smem_desc_sw128(ka + kk * 2048, 8192, 1024);
-          umma_bf16(tmem_base + kColDq, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
+          if (im.issue) umma_bf16(tmem_base + kColDq, a_ds, b_k, idesc_q, kk > 0 ? 1u : 0u);
         }
-        umma_commit(grad_full);
-        umma_commit(&kv_empty[s]);
+        if (im.issue) umma_commit(grad_full);
+        if (im.issue) umma_commit(&kv_empty[s]);
+        im.sync();
       }
     }
   } else {

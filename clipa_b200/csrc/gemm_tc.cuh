@@ -530,7 +530,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
+    const IssueMode im = issue_mode(lane);
+    if (im.in_loop) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -562,16 +563,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                      : make_smem_desc_sw128(sb, 16, 1024);
             constexpr uint32_t a_step = (A_MN ? 2048 : 32) >> 4;
             constexpr uint32_t b_step = (B_MN ? 2048 : 32) >> 4;
+            if (im.issue) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              umma_bf16(d_addr, da + static_cast<uint64_t>(k * a_step),
-                        db + static_cast<uint64_t>(k * b_step), kIdesc,
-                        (kb > kb_begin || k > 0) ? 1u : 0u);
+              for (int k = 0; k < kBK / 16; ++k) {
+                umma_bf16(d_addr, da + static_cast<uint64_t>(k * a_step),
+                          db + static_cast<uint64_t>(k * b_step), kIdesc,
+                          (kb > kb_begin || k > 0) ? 1u : 0u);
+              }
+              umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
             }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            im.sync();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          if (im.issue) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          im.sync();
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }

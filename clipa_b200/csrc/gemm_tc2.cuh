@@ -193,7 +193,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ======================= MMA issuer (leader CTA only) =======================
-    if (leader && lane == 0) {
+    const IssueMode im = issue_mode(lane);
+    if (leader && im.in_loop) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -214,14 +215,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const uint64_t db = B_MN ? make_smem_desc_sw128(sb, kBK * 128, 1024) : make_smem_desc_sw128(sb, 16, 1024);
           constexpr uint32_t a_step = (A_MN ? 2048 : 32) >> 4;
           constexpr uint32_t b_step = (B_MN ? 2048 : 32) >> 4;
+          if (im.issue) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16_2sm(d_addr, da + static_cast<uint64_t>(k * a_step), db + static_cast<uint64_t>(k * b_step),
-                          kIdesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[stage]);
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_2sm(d_addr, da + static_cast<uint64_t>(k * a_step), db + static_cast<uint64_t>(k * b_step),
+                            kIdesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+          }
+          im.sync();
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tmem_full[acc]);
+        if (im.issue) umma_commit_2sm(&tmem_full[acc]);
+        im.sync();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

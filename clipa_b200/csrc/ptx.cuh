@@ -251,6 +251,37 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
 // ----------------------------------------------------------------------------------------------
+// Issue mode of the single-thread instruction streams (tcgen05.mma / commit).
+//   CLIPA_UNIFORM_ISSUE = 0: the issuer is `lane == 0` inside a divergent branch.  The compiler cannot
+//     prove the operands warp-uniform and wraps EVERY tcgen05 instruction in an ELECT /
+//     R2UR.BROADCAST / BRA.U.ANY serialisation loop: 17-19 SASS instructions between consecutive
+//     UTCHMMAs, ~100 per k-block on the thread that feeds the tensor pipe.
+//   CLIPA_UNIFORM_ISSUE = 1: the whole warp runs the (warp-uniform) loop, one elected lane issues;
+//     descriptors live in uniform registers and the four UTCHMMAs of a k-block are back to back.
+// Usage:  const IssueMode im = issue_mode(lane);  if (im.in_loop) { ... if (im.issue) {mma; commit;} im.sync(); }
+// ----------------------------------------------------------------------------------------------
+#ifndef CLIPA_UNIFORM_ISSUE
+#define CLIPA_UNIFORM_ISSUE 0
+#endif
+struct IssueMode {
+  bool in_loop;   // this lane runs the issuer's control flow
+  bool issue;     // this lane executes the tcgen05 instructions
+  __device__ __forceinline__ void sync() const {
+#if CLIPA_UNIFORM_ISSUE
+    __syncwarp();
+#endif
+  }
+};
+// must be called by a converged warp
+__device__ __forceinline__ IssueMode issue_mode(int lane) {
+#if CLIPA_UNIFORM_ISSUE
+  return IssueMode{true, elect_one()};
+#else
+  return IssueMode{lane == 0, true};
+#endif
+}
+
+// ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
