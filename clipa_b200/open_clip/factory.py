@@ -18,7 +18,7 @@ from typing import Any, Dict, Optional, Tuple, Union
 import torch
 
 from .loss import ClipLoss
-from .model import CLIP, convert_weights_to_lp, get_cast_dtype
+from .model import CLIP, convert_weights_to_lp, get_cast_dtype, resize_pos_embed, resize_text_pos_embed
 from .model_configs import add_model_config, get_model_config, list_models  # noqa: F401
 
 OPENAI_DATASET_MEAN = (0.48145466, 0.4578275, 0.40821073)
@@ -35,7 +35,12 @@ def load_state_dict(checkpoint_path: str, map_location='cpu'):
 
 
 def load_checkpoint(model, checkpoint_path, strict=True):
-    return model.load_state_dict(load_state_dict(checkpoint_path), strict=strict)
+    """open_clip/factory.py:110-118: position tables of the checkpoint are resampled to the model's image
+    grid / context length before loading (pre-train at 84-126 px, fine-tune at 224+)."""
+    state_dict = load_state_dict(checkpoint_path)
+    resize_pos_embed(state_dict, model)
+    resize_text_pos_embed(state_dict, model)
+    return model.load_state_dict(state_dict, strict=strict)
 
 
 def create_model(model_name: str, pretrained: Optional[str] = None, precision: str = 'fp32',

@@ -3,6 +3,8 @@ arguments, attributes, parameter names and return conventions; the towers run on
 kernels (clipa_b200.functional)."""
 from __future__ import annotations
 
+import logging
+import math
 from dataclasses import dataclass
 from typing import Optional, Tuple, Union
 
@@ -185,6 +187,43 @@ class CLIP(nn.Module):
             return {"image_features": image_features, "text_features": text_features,
                     "logit_scale": self.logit_scale.exp()}
         return image_features, text_features, self.logit_scale.exp()
+
+
+def resize_pos_embed(state_dict, model, interpolation: str = 'bicubic', antialias: bool = True):
+    """Rescale the learnable image position-embedding grid of a checkpoint to the model's grid when they
+    differ (fine-tuning at a larger resolution; open_clip/model.py:452-483): the CLS row is kept, the
+    patch rows are resampled as a [1, D, g, g] image with F.interpolate(align_corners=False).  In place."""
+    old = state_dict.get('visual.positional_embedding', None)
+    if old is None or not hasattr(model.visual, 'grid_size'):
+        return
+    gh, gw = model.visual.grid_size
+    extra = 1
+    if gh * gw + extra == old.shape[0]:
+        return
+    tok, img = old[:extra], old[extra:]
+    og = int(math.sqrt(len(img)))
+    logging.info('Resizing position embedding grid-size from %s to %s', (og, og), (gh, gw))
+    img = img.reshape(1, og, og, -1).permute(0, 3, 1, 2)
+    img = F.interpolate(img, size=(gh, gw), mode=interpolation, antialias=antialias, align_corners=False)
+    img = img.permute(0, 2, 3, 1).reshape(1, gh * gw, -1)[0]
+    state_dict['visual.positional_embedding'] = torch.cat([tok, img], dim=0)
+
+
+def resize_text_pos_embed(state_dict, model, interpolation: str = 'linear', antialias: bool = False):
+    """Same for the text position table when the context length differs (open_clip/model.py:486-516)."""
+    old = state_dict.get('positional_embedding', None)
+    if old is None:
+        return
+    cur = getattr(model, 'positional_embedding', None)
+    if cur is None:
+        return
+    assert old.shape[1] == cur.shape[1], 'text pos_embed width changed!'
+    if old.shape[0] == cur.shape[0]:
+        return
+    logging.info('Resizing text position embedding num_pos from %s to %s', old.shape[0], cur.shape[0])
+    new = F.interpolate(old.reshape(1, old.shape[0], old.shape[1]).permute(0, 2, 1), size=cur.shape[0],
+                        mode=interpolation, antialias=antialias, align_corners=False)
+    state_dict['positional_embedding'] = new.permute(0, 2, 1)[0]
 
 
 def convert_weights_to_lp(model: nn.Module, dtype=torch.bfloat16):

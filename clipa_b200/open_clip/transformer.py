@@ -37,6 +37,38 @@ class LayerNorm(nn.LayerNorm):
 LayerNormFp32 = LayerNorm
 
 
+class PatchDropout(nn.Module):
+    """Random token dropping of the image sequence in training (open_clip/transformer.py:53-90,
+    arXiv 2212.00794): keeps `max(1, int(num_tokens * (1 - prob)))` patch tokens per sample, chosen as
+    the top-k of i.i.d. normal scores, in top-k ORDER (the reference does not re-sort them; positional
+    embeddings are already added, and the non-causal tower is permutation-equivariant), with the CLS
+    token kept in front.  Identity in eval mode or for prob == 0.
+
+    Unlike the reference, which draws the scores with a default-device `torch.randn` (a host round trip
+    when the activations live on the GPU, transformer.py:76,82), scores are drawn on the activations'
+    device.  `score_fn(batch, num_tokens, device)` can be replaced to inject scores (parity tests)."""
+
+    def __init__(self, prob: float, exclude_first_token: bool = True):
+        super().__init__()
+        assert 0 <= prob < 1.
+        self.prob = prob
+        self.exclude_first_token = exclude_first_token
+        self.score_fn = lambda batch, num_tokens, device: torch.randn(batch, num_tokens, device=device)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:      # [batch, tokens, width]
+        if not self.training or self.prob == 0.:
+            return x
+        if self.exclude_first_token:
+            cls_tokens, x = x[:, :1], x[:, 1:]
+        batch, num_tokens = x.shape[0], x.shape[1]
+        keep = max(1, int(num_tokens * (1 - self.prob)))
+        idx = self.score_fn(batch, num_tokens, x.device).topk(keep, dim=-1).indices
+        x = torch.gather(x, 1, idx.unsqueeze(-1).expand(batch, keep, x.shape[2]))
+        if self.exclude_first_token:
+            x = torch.cat((cls_tokens, x), dim=1)
+        return x
+
+
 class ResidualAttentionBlock(nn.Module):
     """open_clip/transformer.py:195-250 (self-attention form; ls_1/ls_2 are Identity as in every
     shipped CLIPA config)."""
@@ -115,8 +147,8 @@ class VisionTransformer(nn.Module):
                  pos_embed: str = "learnable", ln_pre: bool = True, pool_style: str = "open_clip",
                  output_tokens: bool = False):
         super().__init__()
-        if patch_dropout > 0.:
-            raise NotImplementedError("PatchDropout is a 'next' row of the scope table (SURVEY 8f.4)")
+        # a patch_dropout of 0. means disabled (open_clip/transformer.py:387-388)
+        self.patch_dropout = PatchDropout(patch_dropout) if patch_dropout > 0. else nn.Identity()
         self.output_tokens = output_tokens
         image_height, image_width = self.image_size = to_2tuple(image_size)
         patch_height, patch_width = self.patch_size = to_2tuple(patch_size)
@@ -192,6 +224,7 @@ class VisionTransformer(nn.Module):
         tok = Fn.LinearFn.apply(patches.contiguous(), wmat, None, False).reshape(N, gh * gw, W)
         cls = self.class_embedding.to(tok.dtype).reshape(1, 1, W).expand(N, 1, W)
         x = torch.cat([cls, tok], dim=1) + self.positional_embedding.to(tok.dtype)
+        x = self.patch_dropout(x)          # after the positional embedding, before ln_pre (transformer.py:501-502)
         L = x.shape[1]
         x = self.ln_pre(x)
         x = self.transformer(x.reshape(N * L, W).contiguous(), N, L, causal=False).reshape(N, L, W)

@@ -159,10 +159,48 @@ def make_schema_golden(open_clip):
     print("wrote reference_schema.json")
 
 
+def make_host_ops_golden(open_clip):
+    """Host-side pieces of the input/checkpoint stage run through the reference:
+    PatchDropout (open_clip/transformer.py:53-90) with injected scores, and the position-table
+    resamplers used when a checkpoint is loaded at another resolution / context length
+    (open_clip/model.py:452-516)."""
+    from types import SimpleNamespace
+    from unittest import mock
+    from open_clip.model import resize_pos_embed, resize_text_pos_embed
+    from open_clip.transformer import PatchDropout
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for tag, (b, n, d, prob) in {"pd_a": (3, 17, 8, 0.5), "pd_b": (2, 37, 4, 0.75), "pd_c": (4, 5, 6, 0.9)}.items():
+        x = torch.randn(b, n, d, generator=g)
+        scores = torch.randn(b, n - 1, generator=g)
+        pd = PatchDropout(prob)
+        pd.train()
+        with mock.patch("torch.randn", return_value=scores):
+            y = pd(x)
+        out[f"{tag}_x"], out[f"{tag}_scores"], out[f"{tag}_y"] = x.numpy(), scores.numpy(), y.numpy()
+        out[f"{tag}_prob"] = np.float64(prob)
+    for tag, (og, ng, d) in {"pe_up": (6, 16, 32), "pe_down": (9, 6, 16)}.items():
+        sd = {"visual.positional_embedding": torch.randn(1 + og * og, d, generator=g)}
+        out[f"{tag}_old"] = sd["visual.positional_embedding"].numpy().copy()
+        resize_pos_embed(sd, SimpleNamespace(visual=SimpleNamespace(grid_size=(ng, ng))))
+        out[f"{tag}_new"] = sd["visual.positional_embedding"].numpy()
+    for tag, (ol, nl, d) in {"te_up": (16, 32, 24), "te_down": (77, 16, 8)}.items():
+        sd = {"positional_embedding": torch.randn(ol, d, generator=g)}
+        out[f"{tag}_old"] = sd["positional_embedding"].numpy().copy()
+        resize_text_pos_embed(sd, SimpleNamespace(positional_embedding=torch.zeros(nl, d)))
+        out[f"{tag}_new"] = sd["positional_embedding"].numpy()
+    np.savez_compressed(GOLD / "host_ops_ref.npz", **out)
+    print("wrote host_ops_ref.npz")
+
+
 def main():
     if "--schema-only" in sys.argv:
         GOLD.mkdir(parents=True, exist_ok=True)
         make_schema_golden(import_reference())
+        return
+    if "--host-ops-only" in sys.argv:
+        GOLD.mkdir(parents=True, exist_ok=True)
+        make_host_ops_golden(import_reference())
         return
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
@@ -184,6 +222,7 @@ def main():
             print(f"wrote {name}_{precision}.npz loss={float(res['loss']):.6f} ({loss_dtype})")
     make_ddp_loss_golden()
     make_schema_golden(open_clip)
+    make_host_ops_golden(open_clip)
 
 
 if __name__ == "__main__":

@@ -85,8 +85,10 @@ def test_unsupported_features_raise(tmp_path):
         open_clip.create_model("bad-timm")
     with pytest.raises(NotImplementedError):
         open_clip.create_model("ViT-B-32", precision="fp16")
-    with pytest.raises(NotImplementedError):
-        open_clip.create_model("ViT-B-32", force_patch_dropout=0.5)
+    # PatchDropout is built: the factory override reaches the tower
+    from clipa_b200.open_clip import PatchDropout
+    m = open_clip.create_model("ViT-B-32", force_patch_dropout=0.5)
+    assert isinstance(m.visual.patch_dropout, PatchDropout) and m.visual.patch_dropout.prob == 0.5
 
 
 def test_create_loss_signature():
@@ -142,3 +144,80 @@ def test_gradcache_schedule_matches_single_pass_cpu():
         assert abs(l - grads[0][0]) < 1e-6
         for a, b in zip(g, grads[0][1]):
             assert torch.allclose(a, b, atol=1e-6, rtol=1e-5)
+
+
+def _host_gold():
+    import numpy as np
+    from pathlib import Path
+    return np.load(Path(__file__).parent / "golden" / "host_ops_ref.npz")
+
+
+def test_patch_dropout_matches_reference_golden():
+    """PatchDropout (open_clip/transformer.py:53-90) with the reference's scores injected: same kept tokens in
+    the same (top-k) order, CLS in front; identity in eval mode."""
+    import torch
+    from clipa_b200.open_clip import PatchDropout
+    g = _host_gold()
+    for tag in ("pd_a", "pd_b", "pd_c"):
+        x = torch.from_numpy(g[f"{tag}_x"])
+        scores = torch.from_numpy(g[f"{tag}_scores"])
+        pd = PatchDropout(float(g[f"{tag}_prob"]))
+        pd.score_fn = lambda b, n, dev, s=scores: s
+        pd.train()
+        y = pd(x)
+        assert y.shape == tuple(g[f"{tag}_y"].shape)
+        assert torch.equal(y, torch.from_numpy(g[f"{tag}_y"])), tag
+        pd.eval()
+        assert pd(x) is x
+    # default score_fn draws on the activations' device and keeps max(1, int(n * (1 - p))) patch tokens
+    pd = PatchDropout(0.5)
+    pd.train()
+    y = pd(torch.randn(2, 82, 4))
+    assert y.shape == (2, 1 + int(81 * 0.5), 4)
+
+
+def test_pos_embed_resizers_match_reference_golden():
+    """resize_pos_embed / resize_text_pos_embed (open_clip/model.py:452-516) against the reference's outputs."""
+    import torch
+    from types import SimpleNamespace
+    from clipa_b200.open_clip import resize_pos_embed, resize_text_pos_embed
+    g = _host_gold()
+    for tag in ("pe_up", "pe_down"):
+        new = g[f"{tag}_new"]
+        grid = int(round((new.shape[0] - 1) ** 0.5))
+        sd = {"visual.positional_embedding": torch.from_numpy(g[f"{tag}_old"].copy())}
+        resize_pos_embed(sd, SimpleNamespace(visual=SimpleNamespace(grid_size=(grid, grid))))
+        assert torch.equal(sd["visual.positional_embedding"], torch.from_numpy(new)), tag
+    for tag in ("te_up", "te_down"):
+        new = g[f"{tag}_new"]
+        sd = {"positional_embedding": torch.from_numpy(g[f"{tag}_old"].copy())}
+        resize_text_pos_embed(sd, SimpleNamespace(positional_embedding=torch.zeros(new.shape)))
+        assert torch.equal(sd["positional_embedding"], torch.from_numpy(new)), tag
+    # same grid / length: untouched
+    sd = {"visual.positional_embedding": torch.zeros(1 + 9, 4), "positional_embedding": torch.zeros(16, 4)}
+    keep = sd["visual.positional_embedding"]
+    resize_pos_embed(sd, SimpleNamespace(visual=SimpleNamespace(grid_size=(3, 3))))
+    resize_text_pos_embed(sd, SimpleNamespace(positional_embedding=torch.zeros(16, 4)))
+    assert sd["visual.positional_embedding"] is keep
+
+
+def test_load_checkpoint_resamples_position_tables(tmp_path):
+    """factory.load_checkpoint resamples a checkpoint saved at another image grid / context length
+    (open_clip/factory.py:110-118) instead of failing on the shape mismatch."""
+    import torch
+    from clipa_b200 import open_clip
+    from oracle.weights import TINY_CONFIGS
+    import copy, json
+    cfg = copy.deepcopy(TINY_CONFIGS["tiny-cls"])
+    d = tmp_path / "cfgs"
+    d.mkdir()
+    (d / "ckpt-tiny.json").write_text(json.dumps(cfg))
+    open_clip.add_model_config(d)
+    small = open_clip.create_model("ckpt-tiny", precision="fp32", device="cpu", force_image_size=32)
+    torch.save({"state_dict": {"module." + k: v for k, v in small.state_dict().items()}}, tmp_path / "small.pt")
+    big = open_clip.create_model("ckpt-tiny", precision="fp32", device="cpu", force_image_size=64,
+                                 pretrained=str(tmp_path / "small.pt"))
+    gs, gb = small.visual.grid_size[0], big.visual.grid_size[0]
+    assert gb == 2 * gs and big.visual.positional_embedding.shape[0] == 1 + gb * gb
+    assert torch.equal(big.visual.positional_embedding[0], small.visual.positional_embedding[0])      # CLS row kept
+    assert torch.equal(big.visual.conv1.weight, small.visual.conv1.weight)
