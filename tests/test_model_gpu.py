@@ -221,6 +221,39 @@ def test_gradcache_chunks_match_single_pass(dev, micro):
         assert rel_err(g1[n].cpu(), g0[n].cpu()) < 2e-2, n
 
 
+def test_patch_dropout_runs_on_device(dev):
+    """PatchDropout (open_clip/transformer.py:53-90, pinned on CPU in tests/test_host_logic_cpu.py) inside the
+    CUDA tower: the shortened sequence (CLS + kept patches) goes through the packed-tile attention path;
+    deterministic for fixed scores, identity in eval mode, gradients finite."""
+    from clipa_b200 import open_clip
+    from clipa_b200.open_clip import PatchDropout
+    from oracle.weights import make_inputs
+    meta, _ = load_golden("tiny-cls", "fp32")
+    model = build_model(meta, "amp_bf16", dev)
+    images, text = make_inputs(meta["cfg"], 6, 3, image_size=meta["image_size"])
+    images, text = images.to(dev), text.to(dev)
+    model.eval()
+    with torch.no_grad():
+        base = model(images, text)["image_features"].float()
+    n_patch = model.visual.positional_embedding.shape[0] - 1
+    pd = PatchDropout(0.5)
+    scores = torch.randn(6, n_patch, generator=torch.Generator().manual_seed(5)).to(dev)
+    pd.score_fn = lambda b, n, d: scores
+    model.visual.patch_dropout = pd
+    with torch.no_grad():
+        assert torch.equal(model(images, text)["image_features"].float(), base)     # eval: identity
+    model.train()
+    out1 = model(images, text)
+    with torch.no_grad():
+        out2 = model(images, text)
+    assert torch.equal(out1["image_features"], out2["image_features"])              # same scores -> same tokens
+    assert (out1["image_features"].float() - base).abs().max() > 1e-3                # half the patches are gone
+    loss = open_clip.ClipLoss()(out1["image_features"], out1["text_features"], out1["logit_scale"])
+    loss.backward()
+    g = model.visual.conv1.weight.grad
+    assert g is not None and torch.isfinite(g.float()).all() and g.float().abs().sum() > 0
+
+
 def test_activation_policy_save_ln_equals_recompute(dev):
     """Keeping the LayerNorm outputs for backward (save_ln_outputs) and recomputing them are the same math."""
     from clipa_b200.open_clip.transformer import Transformer
