@@ -221,3 +221,29 @@ def test_load_checkpoint_resamples_position_tables(tmp_path):
     assert gb == 2 * gs and big.visual.positional_embedding.shape[0] == 1 + gb * gb
     assert torch.equal(big.visual.positional_embedding[0], small.visual.positional_embedding[0])      # CLS row kept
     assert torch.equal(big.visual.conv1.weight, small.visual.conv1.weight)
+
+
+def test_grad_sink_is_opt_in():
+    """functional.grad_sink: gradient kernels write straight into `.grad` only for parameters that opted in
+    (TrainStep's flat-buffer views) and whose `.grad` is a contiguous fp32 tensor of the parameter's shape."""
+    import torch
+    from clipa_b200.functional import grad_sink
+    p = torch.nn.Parameter(torch.zeros(4, 8))
+    assert grad_sink(None) is None and grad_sink(p) is None            # no flag
+    p._clipa_direct_grad = True
+    assert grad_sink(p) is None                                          # no .grad yet
+    p.grad = torch.zeros(4, 8)
+    assert grad_sink(p) is p.grad
+    pb = torch.nn.Parameter(torch.zeros(4, 8, dtype=torch.bfloat16))
+    pb._clipa_direct_grad = True
+    pb.grad = torch.zeros(4, 8, dtype=torch.bfloat16)
+    assert grad_sink(pb) is None                                         # only fp32 gradient buffers qualify
+    flat = torch.zeros(64)
+    p.grad = None
+    p.grad = flat[:32].view(4, 8)
+    assert grad_sink(p) is p.grad and grad_sink(p).data_ptr() == flat.data_ptr()
+    q = torch.nn.Parameter(torch.zeros(8, 4))
+    q._clipa_direct_grad = True
+    q.grad = torch.zeros(8, 4)
+    q.grad = q.grad.t().contiguous().t()                                 # non-contiguous view
+    assert grad_sink(q) is None
