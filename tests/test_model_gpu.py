@@ -240,6 +240,7 @@ def test_patch_dropout_runs_on_device(dev):
     scores = torch.randn(6, n_patch, generator=torch.Generator().manual_seed(5)).to(dev)
     pd.score_fn = lambda b, n, d: scores
     model.visual.patch_dropout = pd
+    model.eval()                       # the freshly attached module must follow the model's mode
     with torch.no_grad():
         assert torch.equal(model(images, text)["image_features"].float(), base)     # eval: identity
     model.train()
