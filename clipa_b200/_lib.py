@@ -18,7 +18,7 @@ MAJOR_K, MAJOR_MN = 0, 1
 ACT_GELU_ERF, ACT_GELU_TANH, ACT_QUICK_GELU = 0, 1, 2
 EPI_STORE, EPI_BIAS_ACT, EPI_DACT, EPI_ATOMIC_F32 = 0, 1, 2, 3
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class GemmDesc(C.Structure):
@@ -57,9 +57,11 @@ _SIGNATURES = {
                                       C.c_int32, C.c_void_p]),
     "clipa_attention_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "clipa_attention_bwd_workspace": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "clipa_attention_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                      C.c_void_p]),
+                                      C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_void_p]),
+    "clipa_set_attention_mode": (C.c_int, [C.c_int]),
     "clipa_colsum_accum": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                      C.c_void_p]),
     "clipa_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

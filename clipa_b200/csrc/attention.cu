@@ -437,10 +437,36 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int batch, int L, i
                      cudaStream_t stream);  // attention_tc.cu
 int attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                      int batch, int L, int H, int causal, cudaStream_t stream);
+int attention_fwd_flash(const void* qkv, void* out, float* lse, int batch, int L, int H, int hd, int causal,
+                        cudaStream_t stream);  // attention_flash.cu
+int attention_bwd_flash(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                        void* workspace, long long workspace_bytes, int batch, int L, int H, int hd, int causal,
+                        cudaStream_t stream);
+long long attention_bwd_flash_workspace(int batch, int L, int H, int hd);
+
+// 0 = auto; 1 = mma.sync kernels wherever they take the shape; 2 = flash tcgen05 kernels for every
+// head_dim 64 / 80 shape (also the one-tile shapes attention_tc.cu would take).  Tests and A/B runs only.
+static int g_attn_mode = 0;
+
+enum AttnPath { kPathTc, kPathFlash, kPathMma };
+static AttnPath attn_path(int L, int hd) {
+  const bool flash_ok = hd == 64 || hd == 80;
+  if (g_attn_mode == 1) return kPathMma;
+  if (g_attn_mode == 2 && flash_ok) return kPathFlash;
+  if (hd == 64 && L <= 128) return kPathTc;       // one-tile kernels (packed short sequences, pipelined bwd)
+  if (flash_ok) return kPathFlash;                // L > 128 (224 / 336 px fine-tune) and every ViT-H tower
+  return kPathMma;                                // head_dim 96 / 128
+}
 
 }  // namespace clipa
 
 using namespace clipa;
+
+extern "C" int clipa_set_attention_mode(int mode) {
+  CLIPA_REQUIRE(mode >= 0 && mode <= 2, CLIPA_ERR_BAD_ARG, "clipa_set_attention_mode: mode %d", mode);
+  g_attn_mode = mode;
+  return CLIPA_OK;
+}
 
 extern "C" int clipa_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t L,
                                    int32_t heads, int32_t head_dim, int32_t causal, void* stream) {
@@ -448,9 +474,11 @@ extern "C" int clipa_attention_fwd(const void* qkv, void* out, float* lse, int32
   CLIPA_REQUIRE(batch > 0 && L > 0 && heads > 0, CLIPA_ERR_BAD_ARG, "attention_fwd: bad dims");
   CLIPA_REQUIRE((long long)batch * heads < (1LL << 31), CLIPA_ERR_UNSUPPORTED, "attention_fwd: grid too large");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // tcgen05 tile kernel for the shapes every CLIPA pre-training config uses; the mma.sync kernel
-  // covers long sequences (L > 128, e.g. the 224-px fine-tune stage) and other head widths.
-  if (head_dim == 64 && L <= 128) return attention_fwd_tc(qkv, out, lse, batch, L, heads, causal, s);
+  switch (attn_path(L, head_dim)) {
+    case kPathTc: return attention_fwd_tc(qkv, out, lse, batch, L, heads, causal, s);
+    case kPathFlash: return attention_fwd_flash(qkv, out, lse, batch, L, heads, head_dim, causal, s);
+    default: break;
+  }
   switch (head_dim) {
     case 64: return launch_attn_fwd<64>(qkv, out, lse, batch, L, heads, causal, s);
     case 80: return launch_attn_fwd<80>(qkv, out, lse, batch, L, heads, causal, s);
@@ -462,14 +490,26 @@ extern "C" int clipa_attention_fwd(const void* qkv, void* out, float* lse, int32
   }
 }
 
+extern "C" int64_t clipa_attention_bwd_workspace(int32_t batch, int32_t L, int32_t heads, int32_t head_dim) {
+  if (batch <= 0 || L <= 0 || heads <= 0) return 0;
+  return attn_path(L, head_dim) == kPathFlash ? attention_bwd_flash_workspace(batch, L, heads, head_dim) : 0;
+}
+
 extern "C" int clipa_attention_bwd(const void* qkv, const void* out, const void* dout,
-                                   const float* lse, void* dqkv, int32_t batch, int32_t L,
-                                   int32_t heads, int32_t head_dim, int32_t causal, void* stream) {
+                                   const float* lse, void* dqkv, void* workspace, int64_t workspace_bytes,
+                                   int32_t batch, int32_t L, int32_t heads, int32_t head_dim, int32_t causal,
+                                   void* stream) {
   CLIPA_REQUIRE(qkv && out && dout && lse && dqkv, CLIPA_ERR_BAD_ARG, "attention_bwd: null pointer");
   CLIPA_REQUIRE(batch > 0 && L > 0 && heads > 0, CLIPA_ERR_BAD_ARG, "attention_bwd: bad dims");
   CLIPA_REQUIRE((long long)batch * heads < (1LL << 31), CLIPA_ERR_UNSUPPORTED, "attention_bwd: grid too large");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (head_dim == 64 && L <= 128) return attention_bwd_tc(qkv, out, dout, lse, dqkv, batch, L, heads, causal, s);
+  switch (attn_path(L, head_dim)) {
+    case kPathTc: return attention_bwd_tc(qkv, out, dout, lse, dqkv, batch, L, heads, causal, s);
+    case kPathFlash:
+      return attention_bwd_flash(qkv, out, dout, lse, dqkv, workspace, workspace_bytes, batch, L, heads, head_dim,
+                                 causal, s);
+    default: break;
+  }
   switch (head_dim) {
     case 64: return launch_attn_bwd<64>(qkv, out, dout, lse, dqkv, batch, L, heads, causal, s);
     case 80: return launch_attn_bwd<80>(qkv, out, dout, lse, dqkv, batch, L, heads, causal, s);

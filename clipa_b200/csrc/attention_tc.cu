@@ -20,6 +20,7 @@
 // chunks its rows' blocks overlap, so the work per sample does not grow with the packing.
 #include <type_traits>
 
+#include "attn_common.cuh"
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -27,9 +28,7 @@ namespace clipa {
 
 constexpr int kTcHd = 64;
 constexpr int kTcThreads = 320;
-constexpr int kTcTileBytes = 128 * 128;                     // 128 rows x 128 B
 constexpr int kTcStageBytes = 3 * kTcTileBytes;             // Q, K, V
-constexpr int kTcPBytes = 2 * kTcTileBytes;                 // P: 128 rows x 128 keys bf16 = 2 swizzle atoms
 // Q/K/V smem ring: 3 slots for one-sample tiles, 2 for packed tiles (which then keep 63 KB of L1 for
 // their all-rows-active output stores; with the 3-slot footprint they ran 10 % slower)
 constexpr int tc_ring(bool packed) { return packed ? 2 : 3; }
@@ -68,25 +67,6 @@ __device__ __forceinline__ RowSpan row_span(int row, int L, int GL) {
   r.token = rr - r.lo;
   r.hi = CAUSAL ? rr + 1 : r.lo + L;
   return r;
-}
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ uint4 pack8_bf16(const float* f) {
-  uint4 t;
-  t.x = pack_bf16x2(f[0], f[1]);
-  t.y = pack_bf16x2(f[2], f[3]);
-  t.z = pack_bf16x2(f[4], f[5]);
-  t.w = pack_bf16x2(f[6], f[7]);
-  return t;
-}
-// byte offset of 16-byte chunk `chunk` (along the key axis) of row `row` in a [128 x 128-key] bf16
-// tile stored as two 128B-swizzled atoms of 64 keys
-__device__ __forceinline__ uint32_t p_tile_off(int row, int chunk) {
-  return (chunk >> 3) * kTcTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
 }
 
 // NCH = 32-column chunks of the score row held in registers; PACKED = more than one sample per tile

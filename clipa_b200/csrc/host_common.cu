@@ -66,7 +66,9 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint6
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  swizzle_bytes == 32   ? CU_TENSOR_MAP_SWIZZLE_32B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                        : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CLIPA_REQUIRE(r == CUDA_SUCCESS, CLIPA_ERR_CUDA,
                 "cuTensorMapEncodeTiled failed (CUresult %d; dims %llu x %llu pitch %llu box %u x %u)",

@@ -15,7 +15,7 @@ void count_launch(int n = 1);
 int num_sms();
 
 // Encodes a 2-D bf16 tensor map: dim0 = contiguous (inner) extent, dim1 = outer extent,
-// row pitch in bytes, box = {box0, box1}, 128- or 64-byte swizzle, OOB reads fill zeros / OOB
+// row pitch in bytes, box = {box0, box1}, 128-, 64- or 32-byte swizzle, OOB reads fill zeros / OOB
 // writes are clipped.
 // Returns CLIPA_OK or an error (message set).
 int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1,

@@ -149,6 +149,20 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same descriptor format with the 32-byte swizzle (layout type 6): rows of 32 B (16 bf16), 8-row groups
+// `sbo_bytes` (= 256 when rows are packed) apart.  K-major: one atom spans the K = 16 of one MMA;
+// MN-major: one atom holds 16 MN elements, `lbo_bytes` apart.  Used for the 16-column remainder of
+// head_dim 80 (64 + 16) next to the 128B-swizzled main tile.
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                        uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
 // Instruction descriptor (32-bit) for kind::f16 with bf16 A/B and fp32 accumulate.
 //   [4,6) D fmt = 1 (f32)  [7,10) A fmt = 1 (bf16)  [10,13) B fmt = 1 (bf16)
 //   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4
@@ -261,7 +275,7 @@ __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 // Usage:  const IssueMode im = issue_mode(lane);  if (im.in_loop) { ... if (im.issue) {mma; commit;} im.sync(); }
 // ----------------------------------------------------------------------------------------------
 #ifndef CLIPA_UNIFORM_ISSUE
-#define CLIPA_UNIFORM_ISSUE 0
+#define CLIPA_UNIFORM_ISSUE 1
 #endif
 struct IssueMode {
   bool in_loop;   // this lane runs the issuer's control flow

@@ -182,9 +182,11 @@ def attention_bwd(qkv, out, dout, lse, batch: int, L: int, heads: int, causal: b
     hd = D // heads
     assert dout.is_contiguous() and out.is_contiguous() and qkv.is_contiguous()
     dqkv = torch.empty_like(qkv)
+    nws = int(_lib.lib().clipa_attention_bwd_workspace(batch, L, heads, hd))
+    ws = torch.empty(nws, dtype=torch.uint8, device=qkv.device) if nws else None
     with _prof(("attn_bwd", L, hd, int(causal)), 10.0 * batch * heads * L * L * hd, 16.0 * batch * L * D):
         check(_lib.lib().clipa_attention_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv),
-                                             batch, L, heads, hd, int(causal), _stream()),
+                                             _ptr(ws), nws, batch, L, heads, hd, int(causal), _stream()),
               "clipa_attention_bwd")
     return dqkv
 

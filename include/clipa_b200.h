@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CLIPA_B200_ABI_VERSION 1
+#define CLIPA_B200_ABI_VERSION 2
 
 typedef enum clipa_status {
   CLIPA_OK = 0,
@@ -111,9 +111,19 @@ int clipa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const 
  * additive -inf upper-triangular mask (open_clip/transformer.py:618-624). */
 int clipa_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t L,
                         int32_t heads, int32_t head_dim, int32_t causal, void* stream);
+/* Backward of the same call site (autograd of F.multi_head_attention_forward's SDPA): dqkv bf16
+ * [batch*L, 3*D] receives dQ | dK | dV.  Sequences longer than one tile (L > 128, the 224/336-px
+ * fine-tune stages) sum the dQ partials of their key tiles through a caller-provided fp32
+ * workspace of clipa_attention_bwd_workspace() bytes (0 for one-tile shapes: pass NULL, 0). */
+int64_t clipa_attention_bwd_workspace(int32_t batch, int32_t L, int32_t heads, int32_t head_dim);
 int clipa_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
-                        void* dqkv, int32_t batch, int32_t L, int32_t heads, int32_t head_dim,
-                        int32_t causal, void* stream);
+                        void* dqkv, void* workspace, int64_t workspace_bytes, int32_t batch, int32_t L,
+                        int32_t heads, int32_t head_dim, int32_t causal, void* stream);
+/* Kernel selection for the attention core: 0 = auto (tcgen05 one-tile kernels for head_dim 64 and
+ * L <= 128, tcgen05 flash kernels for any L with head_dim 64 / 80, mma.sync kernels for head_dim
+ * 96 / 128), 1 = mma.sync kernels, 2 = flash kernels wherever head_dim is 64 / 80.  Process-wide;
+ * tests and A/B measurements. */
+int clipa_set_attention_mode(int mode);
 
 /* ---- column sums (bias gradients): out[n] += sum_m x[m,n]; x bf16 [rows, N], out f32 -------- */
 int clipa_colsum_accum(const void* x, int64_t ldx, float* out, int64_t rows, int32_t N,

@@ -161,6 +161,19 @@ def test_colsum(dev):
                                              (40, 82, 16, 64, False), (37, 96, 8, 64, True), (3, 70, 4, 64, True),
                                              (75, 65, 4, 64, False)])
 def test_attention(dev, B, L, H, hd, causal):
+    _attention_case(dev, B, L, H, hd, causal)
+
+
+@pytest.fixture
+def flash_mode():
+    """Force the flash tcgen05 kernels (attention_flash.cu) for every head_dim 64 / 80 shape."""
+    from clipa_b200 import _lib
+    _lib.check(_lib.lib().clipa_set_attention_mode(2), "set_attention_mode")
+    yield
+    _lib.check(_lib.lib().clipa_set_attention_mode(0), "set_attention_mode")
+
+
+def _attention_case(dev, B, L, H, hd, causal, tol_out=2e-2, tol_grad=3e-2):
     o = ops()
     torch.manual_seed(B * 100 + L)
     D = H * hd
@@ -172,14 +185,62 @@ def test_attention(dev, B, L, H, hd, causal):
     if causal:
         s = s + torch.full((L, L), float("-inf"), device=dev).triu(1)
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * L, D)
-    assert relmax(out, ref) < 2e-2
+    assert relmax(out, ref) < tol_out
     assert relmax(lse, torch.logsumexp(s, -1)) < 1e-4
     dout = mk((B * L, D), dev)
     ref.backward(dout.float())
     dqkv = o.attention_bwd(qkv, out, dout, lse, B, L, H, causal)
     gref = x.grad.reshape(B * L, 3 * D)
     for i in range(3):
-        assert relmax(dqkv[:, i * D:(i + 1) * D], gref[:, i * D:(i + 1) * D]) < 3e-2
+        assert relmax(dqkv[:, i * D:(i + 1) * D], gref[:, i * D:(i + 1) * D]) < tol_grad
+
+
+# Flash tcgen05 kernels: every BASELINE shape outside the one-tile kernels -- L = 257 (config 4: 3 tiles of
+# 86), head_dim 80 (config 5 at L = 37; ViT-H fine-tune at 257) -- plus 336-px fine-tune lengths (577 = 7
+# tiles of 83, 401), tile-boundary lengths, causal multi-tile masks, more work items than CTAs, and
+# (forced) the one-tile shapes themselves.
+@pytest.mark.parametrize("B,L,H,hd,causal", [
+    (2, 257, 4, 64, False), (2, 37, 16, 80, False), (2, 257, 4, 80, False), (1, 577, 2, 64, False),
+    (1, 577, 2, 80, False), (2, 401, 2, 64, False), (3, 129, 4, 64, False), (2, 192, 2, 64, True),
+    (2, 193, 2, 80, True), (2, 97, 4, 80, False), (3, 96, 4, 80, True), (5, 82, 16, 64, False),
+    (2, 16, 12, 64, True), (3, 8, 16, 80, True), (1, 1, 2, 80, False), (40, 257, 16, 64, False),
+    (700, 37, 16, 80, False), (30, 65, 16, 80, False), (9, 128, 8, 64, True)])
+def test_attention_flash(dev, flash_mode, B, L, H, hd, causal):
+    _attention_case(dev, B, L, H, hd, causal)
+
+
+def test_attention_flash_is_the_default_for_long_and_wide(dev):
+    """Without any override the BASELINE shapes with L > 128 or head_dim 80 take the tcgen05 flash kernels:
+    same results as the forced path, bit for bit."""
+    from clipa_b200 import _lib
+    o = ops()
+    for (B, L, H, hd) in ((2, 257, 4, 64), (3, 37, 16, 80)):
+        qkv = mk((B * L, 3 * H * hd), dev, seed=L)
+        out0, lse0 = o.attention_fwd(qkv, B, L, H, False)
+        _lib.check(_lib.lib().clipa_set_attention_mode(2), "set_attention_mode")
+        out2, lse2 = o.attention_fwd(qkv, B, L, H, False)
+        _lib.check(_lib.lib().clipa_set_attention_mode(1), "set_attention_mode")
+        out1, _ = o.attention_fwd(qkv, B, L, H, False)          # mma.sync kernels: close, not identical
+        _lib.check(_lib.lib().clipa_set_attention_mode(0), "set_attention_mode")
+        assert torch.equal(out0, out2) and torch.equal(lse0, lse2)
+        assert relmax(out1, out0) < 2e-2
+
+
+def test_attention_uniform_values_long(dev):
+    """Size-independent property at the config-4 per-layer shape (L = 257, 16 heads; 256 samples): identical
+    value rows -> attention returns that row; and d(qkv) of a constant upstream gradient has zero dQ, dK
+    (softmax rows sum to one, so constant values carry no score gradient)."""
+    o = ops()
+    B, L, H, hd = 256, 257, 16, 64
+    D = H * hd
+    qkv = mk((B * L, 3 * D), dev)
+    vrow = torch.randn(D, device=dev).bfloat16()
+    qkv[:, 2 * D:] = vrow
+    out, lse = o.attention_fwd(qkv, B, L, H, False)
+    assert relmax(out, vrow.float().expand(B * L, D)) < 1e-2
+    dout = mk((B * L, D), dev)
+    dqkv = o.attention_bwd(qkv, out, dout, lse, B, L, H, False)
+    assert dqkv[:, :2 * D].float().abs().max().item() < 2e-2 * dout.float().abs().max().item()
 
 
 def test_attention_uniform_values(dev):
