@@ -24,7 +24,8 @@ import torch
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from oracle.weights import CONFIG1, TINY_CONFIGS, make_inputs, make_state_dict  # noqa: E402
+from oracle.weights import (BASELINE_DIM_BATCH, BASELINE_DIM_CASES, CONFIG1, TINY_CONFIGS, make_inputs,  # noqa: E402
+                            make_state_dict)
 
 REF = "/root/reference/clipa_torch"
 GOLD = ROOT / "tests" / "golden"
@@ -53,7 +54,12 @@ CASES = [
 ]
 
 
-def run_reference(open_clip, name, cfg, batch, image_size, pos_embed, seed, precision):
+def run_reference(open_clip, name, cfg, batch, image_size, pos_embed, seed, precision, compact=False):
+    """precision: 'fp32' | 'bf16' (pure bf16 weights, open_clip/model.py:78-86) | 'amp_bf16' (fp32 master
+    weights, forward + loss under bf16 autocast: training/precision.py:11-13 selects
+    torch.cuda.amp.autocast(dtype=bfloat16) -- a no-op without CUDA, so the same context is opened for the CPU
+    device, the closest same-mode run the reference can do in this container).
+    compact: store 64x64 corners instead of whole projection gradients (BASELINE-dimension cases)."""
     tmp = Path(tempfile.mkdtemp())
     (tmp / f"golden-{name}.json").write_text(json.dumps(cfg))
     open_clip.add_model_config(tmp)
@@ -67,9 +73,12 @@ def run_reference(open_clip, name, cfg, batch, image_size, pos_embed, seed, prec
     images, text = make_inputs(cfg, batch, seed + 1000, image_size=image_size)
     if precision == "bf16":
         images = images.to(torch.bfloat16)
-    out = model(images, text)
+    import contextlib
+    ctx = torch.autocast(device_type="cpu", dtype=torch.bfloat16) if precision == "amp_bf16" else contextlib.nullcontext()
     loss_fn = open_clip.ClipLoss()
-    loss = loss_fn(out["image_features"], out["text_features"], out["logit_scale"])
+    with ctx:
+        out = model(images, text)
+        loss = loss_fn(out["image_features"], out["text_features"], out["logit_scale"])
     for p in model.parameters():
         p.grad = None
     out["image_features"].retain_grad()
@@ -86,8 +95,9 @@ def run_reference(open_clip, name, cfg, batch, image_size, pos_embed, seed, prec
         "d_image_features": out["image_features"].grad.float().numpy(),
         "d_text_features": out["text_features"].grad.float().numpy(),
         "g_logit_scale": g["logit_scale"].grad.float().numpy(),
-        "g_visual_proj": g["visual.proj"].grad.float().numpy(),
-        "g_text_projection": g["text_projection"].grad.float().numpy(),
+        "g_visual_proj": g["visual.proj"].grad.float().numpy()[:64, :64] if compact else g["visual.proj"].grad.float().numpy(),
+        "g_text_projection": g["text_projection"].grad.float().numpy()[:64, :64] if compact else g["text_projection"].grad.float().numpy(),
+        "g_visual_proj_norm": np.array(g["visual.proj"].grad.float().norm().item()),
         "g_v0_in_proj_weight": g["visual.transformer.resblocks.0.attn.in_proj_weight"].grad.float().numpy()[:64, :64],
         "g_v0_in_proj_bias": g["visual.transformer.resblocks.0.attn.in_proj_bias"].grad.float().numpy(),
         "g_vlast_c_fc_bias": g[f"visual.transformer.resblocks.{cfg['vision_cfg']['layers'] - 1}.mlp.c_fc.bias"].grad.float().numpy(),
@@ -193,7 +203,38 @@ def make_host_ops_golden(open_clip):
     print("wrote host_ops_ref.npz")
 
 
+def make_baseline_dim_goldens(open_clip):
+    """fp32 and amp_bf16 reference runs at the BASELINE widths / head shapes / sequence lengths."""
+    for i, (name, (cfg, image_size, pos_embed)) in enumerate(BASELINE_DIM_CASES.items()):
+        for precision in ("fp32", "amp_bf16"):
+            seed = 31 + i
+            res = run_reference(open_clip, name, cfg, BASELINE_DIM_BATCH, image_size, pos_embed, seed, precision,
+                                compact=True)
+            meta = {"name": name, "batch": BASELINE_DIM_BATCH, "image_size": image_size, "pos_embed": pos_embed,
+                    "seed": seed, "precision": precision, "cfg": cfg, "compact": True}
+            meta["loss_dtype"] = res.pop("loss_dtype")
+            np.savez_compressed(GOLD / f"{name}_{precision}.npz", meta=json.dumps(meta), **res)
+            print(f"wrote {name}_{precision}.npz loss={float(res['loss']):.6f} ({meta['loss_dtype']})", flush=True)
+
+
+def make_amp_goldens_small(open_clip):
+    """amp_bf16 runs of the small cases (same-mode reference for the benchmarked precision)."""
+    for (name, cfg, batch, image_size, pos_embed, seed) in CASES:
+        res = run_reference(open_clip, name, cfg, batch, image_size, pos_embed, seed, "amp_bf16")
+        meta = {"name": name, "batch": batch, "image_size": image_size, "pos_embed": pos_embed,
+                "seed": seed, "precision": "amp_bf16", "cfg": cfg}
+        meta["loss_dtype"] = res.pop("loss_dtype")
+        np.savez_compressed(GOLD / f"{name}_amp_bf16.npz", meta=json.dumps(meta), **res)
+        print(f"wrote {name}_amp_bf16.npz loss={float(res['loss']):.6f} ({meta['loss_dtype']})", flush=True)
+
+
 def main():
+    if "--baseline-dims-only" in sys.argv:
+        torch.set_num_threads(os.cpu_count())
+        oc = import_reference()
+        make_amp_goldens_small(oc)
+        make_baseline_dim_goldens(oc)
+        return
     if "--schema-only" in sys.argv:
         GOLD.mkdir(parents=True, exist_ok=True)
         make_schema_golden(import_reference())
@@ -220,6 +261,8 @@ def main():
             meta["loss_dtype"] = loss_dtype
             np.savez_compressed(GOLD / f"{name}_{precision}.npz", meta=json.dumps(meta), **res)
             print(f"wrote {name}_{precision}.npz loss={float(res['loss']):.6f} ({loss_dtype})")
+    make_amp_goldens_small(open_clip)
+    make_baseline_dim_goldens(open_clip)
     make_ddp_loss_golden()
     make_schema_golden(open_clip)
     make_host_ops_golden(open_clip)

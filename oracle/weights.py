@@ -131,3 +131,28 @@ TINY_CONFIGS = {
 CONFIG1 = {"embed_dim": 512,
            "vision_cfg": {"image_size": 224, "layers": 12, "width": 768, "patch_size": 32},
            "text_cfg": {"context_length": 16, "vocab_size": 49408, "width": 512, "heads": 8, "layers": 12}}
+
+
+# BASELINE.json configs[1..4] with their real widths / head shapes / sequence lengths and REDUCED DEPTH
+# (so that the reference finishes on CPU in seconds and the fixtures stay small), batch 32:
+#   name -> (cfg, image_size, pos_embed)
+def _baseline_dims(vw, vheadw, patch, tw, theads, ctx, embed, vlayers=2, tlayers=2, **vis):
+    v = {"image_size": 224, "layers": vlayers, "width": vw, "patch_size": patch}
+    if vheadw != 64:
+        v["head_width"] = vheadw
+    v.update(vis)
+    return {"embed_dim": embed, "vision_cfg": v,
+            "text_cfg": {"context_length": ctx, "vocab_size": 49408, "width": tw, "heads": theads, "layers": tlayers}}
+
+
+BASELINE_DIM_CASES = {
+    # configs[2]: ViT-L/14, 126 px -> 81 patches + CLS = 82 tokens (16 x 64 heads), 16 text tokens
+    "vitl14-i81-t16-d2": (_baseline_dims(1024, 64, 14, 768, 12, 16, 768), 126, "sin_cos_2d"),
+    # configs[3]: ViT-L/14 fine-tune, 224 px -> 257 tokens (3 attention tiles), 32 text tokens, learnable pos
+    "vitl14-i256-t32-d2": (_baseline_dims(1024, 64, 14, 768, 12, 32, 768), 224, "learnable"),
+    # configs[4]: ViT-H/14 (head_dim 80), 84 px -> 37 tokens, 8 text tokens, GAP
+    "vith14-i36-t8-d2": (_baseline_dims(1280, 80, 14, 1024, 16, 8, 1024, global_average_pool=True), 84, "sin_cos_2d"),
+    # configs[1]: ViT-B/16, 128 px -> 65 tokens, 16 text tokens
+    "vitb16-i64-t16-d3": (_baseline_dims(768, 64, 16, 512, 8, 16, 512, vlayers=3, tlayers=3), 128, "sin_cos_2d"),
+}
+BASELINE_DIM_BATCH = 32

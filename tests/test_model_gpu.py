@@ -113,6 +113,52 @@ def test_step_matches_reference(dev, name, precision):
     assert loss.dtype == torch.float32
 
 
+BASELINE_DIM = ["vitl14-i81-t16-d2", "vitl14-i256-t32-d2", "vith14-i36-t8-d2", "vitb16-i64-t16-d3"]
+
+
+@pytest.mark.parametrize("name", BASELINE_DIM)
+def test_step_matches_reference_amp_bf16_baseline_dims(dev, name):
+    """north_star parity bar, same mode, BASELINE dimensions: the CUDA step in amp_bf16 against the reference's
+    own amp_bf16 run (fp32 master weights + bf16 autocast, tests/golden/*_amp_bf16.npz) at ViT-L/14 (82 and
+    257 tokens), ViT-H/14 (head_dim 80) and ViT-B/16 shapes, reduced depth, batch 32:
+      loss within 1e-3 relative of the same-mode reference loss (and of the fp32 reference loss);
+      features / gradients within 2x the reference's own amp-vs-fp32 deviation (+2e-3) of the fp32 run."""
+    meta, g32 = load_golden(name, "fp32")
+    _, ga = load_golden(name, "amp_bf16")
+    model, text, out, loss = run_ours(meta, "amp_bf16", dev)
+    params = dict(model.named_parameters())
+    last = meta["cfg"]["vision_cfg"]["layers"] - 1
+    rows = torch.as_tensor(g32["token_rows_idx"])
+    ours = {
+        "image_features": out["image_features"].detach().float().cpu(),
+        "text_features": out["text_features"].detach().float().cpu(),
+        "d_image_features": out["image_features"].grad.float().cpu(),
+        "d_text_features": out["text_features"].grad.float().cpu(),
+        "g_visual_proj": params["visual.proj"].grad.float().cpu()[:64, :64],
+        "g_text_projection": params["text_projection"].grad.float().cpu()[:64, :64],
+        "g_v0_in_proj_weight": params["visual.transformer.resblocks.0.attn.in_proj_weight"].grad.float().cpu()[:64, :64],
+        "g_v0_in_proj_bias": params["visual.transformer.resblocks.0.attn.in_proj_bias"].grad.float().cpu(),
+        "g_vlast_c_fc_bias": params[f"visual.transformer.resblocks.{last}.mlp.c_fc.bias"].grad.float().cpu(),
+        "g_t0_ln_1_weight": params["transformer.resblocks.0.ln_1.weight"].grad.float().cpu(),
+        "g_class_embedding": params["visual.class_embedding"].grad.float().cpu(),
+        "g_token_rows": params["token_embedding.weight"].grad.float().cpu()[rows],
+    }
+    rec = {"case": name, "precision": "amp_bf16", "same_mode_reference": True, "batch": meta["batch"], "errors": {}}
+    failures = []
+    for k, v in ours.items():
+        e_ours, e_ref = rel_err(v, g32[k]), rel_err(ga[k], g32[k])
+        rec["errors"][k] = {"ours_vs_ref_fp32": e_ours, "ref_amp_vs_ref_fp32": e_ref, "ours_vs_ref_amp": rel_err(v, ga[k])}
+        if not e_ours <= 2.0 * e_ref + 2e-3:
+            failures.append((k, e_ours, e_ref))
+    l32, la = float(g32["loss"]), float(ga["loss"])
+    rec["loss"] = {"ours": loss.item(), "ref_fp32": l32, "ref_amp_bf16": la, "rel_err_vs_amp": abs(loss.item() - la) / la,
+                   "rel_err_vs_fp32": abs(loss.item() - l32) / l32, "ref_amp_vs_fp32": abs(la - l32) / l32}
+    _report(rec)
+    assert rec["loss"]["rel_err_vs_amp"] <= 1e-3, rec["loss"]
+    assert rec["loss"]["rel_err_vs_fp32"] <= 1e-3, rec["loss"]
+    assert not failures, failures
+
+
 @pytest.mark.parametrize("name", CASES[:3])
 def test_step_matches_oracle_features(dev, name):
     """Same weights and inputs through the CPU oracle (fp32) and the CUDA path (bf16)."""
