@@ -96,14 +96,26 @@ __device__ __forceinline__ void flash_mma_a_k_b_mn(uint32_t d, uint32_t a_tile, 
   }
 }
 
+// (item, key tile) position of a step; advance() returns true when it moved on to the next item
+struct StepCursor {
+  int it, j, T;
+  int n, h, i;     // decoded item: sample, head, query tile
+  __device__ __forceinline__ void init(int tiles) { it = 0; j = 0; T = tiles; n = h = i = 0; }
+  __device__ __forceinline__ bool advance() {
+    if (++j == T) { j = 0; ++it; return true; }
+    return false;
+  }
+};
+
 // named barrier shared by the two warps (column halves) of one TMEM lane quarter
 __device__ __forceinline__ void pair_sync(int q) {
   asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
 }
 
-// Schedule (k = running step index over all (item, key tile) pairs of this CTA; S and P are double
-// buffered by step parity, O_j has one TMEM buffer):
-//   MMA    : S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ...        PV(k) after p_full(k) and o_read(k-1)
+// Schedule (k = running step index over all (item, key tile) pairs of this CTA; S, P and O_j are double
+// buffered by step parity -- with a single O_j buffer P V(k+1) had to wait for the workers to read O_j(k)
+// and sat on their critical path: 20 % of the worker samples waited on o_full, ncu source view r02):
+//   MMA    : S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ...        PV(k) after p_full(k) and o_read(k-2)
 //   workers: softmax(0) | softmax(1) O(0) | softmax(2) O(1) | ...
 // so the score tile of step k+1 is already in TMEM when the workers finish step k, and P V of step k
 // runs under the softmax of step k+1.  K_j rides 2 steps ahead of V_j in the TMA stream (its slot is
@@ -126,9 +138,9 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
   uint64_t* q_empty = bars + 10;       // [2] last S of the item done
   uint64_t* s_full = bars + 12;        // [2] S in TMEM
   uint64_t* p_full = bars + 14;        // [2] P in smem, S consumed (8 warp arrivals)
-  uint64_t* o_full = bars + 16;        // O_j in TMEM
-  uint64_t* o_read = bars + 17;        // O_j read out (8 warp arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* o_full = bars + 16;        // [2] O_j in TMEM
+  uint64_t* o_read = bars + 18;        // [2] O_j read out (8 warp arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
   float* xmax = reinterpret_cast<float*>(smem + Sm::kXOff);   // [step parity][half][row]
   float* xsum = xmax + 2 * 2 * 128;                            // [half][row]
 
@@ -153,9 +165,9 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 8);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_read[i], 8);
     }
-    mbar_init(o_full, 1);
-    mbar_init(o_read, 8);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -163,7 +175,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr uint32_t kColO = 256;      // S buffers at columns 0 and 128
+  constexpr uint32_t kColO = 256;      // S buffers at columns 0 and 128, O_j buffers at 256 and 384
 
   const int n_local = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int K = n_local * T;           // steps of this CTA
@@ -179,32 +191,33 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
 
   if (warp == 0) {
     if (lane == 0) {
-      auto load_k = [&](int k) {
-        const int it = k / T, j = k - it * T;
-        int n, h, i;
-        decode(it, n, h, i);
-        if (j == 0) {
-          const int b = it & 1;
-          mbar_wait(&q_empty[b], ((it >> 1) & 1) ^ 1);
+      // step cursors (item, key tile) advance incrementally: no integer division per step
+      StepCursor ck, cv;
+      ck.init(T); cv.init(T);
+      if (K > 0) decode(0, ck.n, ck.h, ck.i);
+      cv.n = ck.n; cv.h = ck.h; cv.i = ck.i;
+      auto load_k = [&](int k) {      // k == ck's step
+        if (ck.j == 0) {
+          const int b = ck.it & 1;
+          mbar_wait(&q_empty[b], ((ck.it >> 1) & 1) ^ 1);
           mbar_expect_tx(&q_full[b], (uint32_t)Rt * Tl::kRowBytes);
-          flash_load_op<HD>(smem + Sm::kQOff + b * Tl::kOpBytes, &tmap_main, &tmap_rem, &q_full[b], h * HD,
-                            n * L + i * Rt);
+          flash_load_op<HD>(smem + Sm::kQOff + b * Tl::kOpBytes, &tmap_main, &tmap_rem, &q_full[b], ck.h * HD,
+                            ck.n * L + ck.i * Rt);
         }
         const int s = k & 1;
         mbar_wait(&k_empty[s], ((k >> 1) & 1) ^ 1);
         mbar_expect_tx(&k_full[s], (uint32_t)Rt * Tl::kRowBytes);
-        flash_load_op<HD>(smem + Sm::kKOff + s * Tl::kOpBytes, &tmap_main, &tmap_rem, &k_full[s], D + h * HD,
-                          n * L + j * Rt);
+        flash_load_op<HD>(smem + Sm::kKOff + s * Tl::kOpBytes, &tmap_main, &tmap_rem, &k_full[s], D + ck.h * HD,
+                          ck.n * L + ck.j * Rt);
+        if (ck.advance() && ck.it < n_local) decode(ck.it, ck.n, ck.h, ck.i);
       };
-      auto load_v = [&](int k) {
-        const int it = k / T, j = k - it * T;
-        int n, h, i;
-        decode(it, n, h, i);
+      auto load_v = [&](int k) {      // k == cv's step
         const int s = k & 1;
         mbar_wait(&v_empty[s], ((k >> 1) & 1) ^ 1);
         mbar_expect_tx(&v_full[s], (uint32_t)Rt * Tl::kRowBytes);
-        flash_load_op<HD>(smem + Sm::kVOff + s * Tl::kOpBytes, &tmap_main, &tmap_rem, &v_full[s], 2 * D + h * HD,
-                          n * L + j * Rt);
+        flash_load_op<HD>(smem + Sm::kVOff + s * Tl::kOpBytes, &tmap_main, &tmap_rem, &v_full[s], 2 * D + cv.h * HD,
+                          cv.n * L + cv.j * Rt);
+        if (cv.advance() && cv.it < n_local) decode(cv.it, cv.n, cv.h, cv.i);
       };
       if (K > 0) load_k(0);
       if (K > 1) load_k(1);
@@ -220,8 +233,11 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
       const uint32_t idesc_o64 = make_idesc_bf16(128, 64, false, true);
       const uint32_t idesc_o16 = make_idesc_bf16(128, 16, false, true);
       const int ksteps = p.npad / 16;
-      auto issue_s = [&](int k) {
-        const int it = k / T, j = k - it * T, s = k & 1, b = it & 1;
+      StepCursor cs;
+      cs.init(T);
+      auto issue_s = [&](int k) {     // k == cs's step
+        const int it = cs.it, j = cs.j, s = k & 1, b = it & 1;
+        cs.advance();
         mbar_wait(&k_full[s], (k >> 1) & 1);
         if (j == 0) mbar_wait(&q_full[b], (it >> 1) & 1);
         tc_fence_after();
@@ -236,14 +252,14 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
       if (K > 1) issue_s(1);
       for (int k = 0; k < K; ++k) {
         const int s = k & 1;
-        mbar_wait(&p_full[s], (k >> 1) & 1);          // P(k) written, S(k) consumed
-        if (k > 0) mbar_wait(o_read, (k - 1) & 1);    // O(k-1) read out of TMEM
+        mbar_wait(&p_full[s], (k >> 1) & 1);                  // P(k) written, S(k) consumed
+        if (k > 1) mbar_wait(&o_read[s], ((k >> 1) & 1) ^ 1);  // O(k-2) read out of this TMEM buffer
         mbar_wait(&v_full[s], (k >> 1) & 1);
         tc_fence_after();
-        flash_mma_a_k_b_mn<HD>(tmem_base + kColO, smem_u32(smem + Sm::kPOff + s * kTcPBytes),
+        flash_mma_a_k_b_mn<HD>(tmem_base + kColO + s * 128, smem_u32(smem + Sm::kPOff + s * kTcPBytes),
                                smem_u32(smem + Sm::kVOff + s * Tl::kOpBytes), ksteps, idesc_o64, idesc_o16, false,
                                im.issue);
-        if (im.issue) umma_commit(o_full);
+        if (im.issue) umma_commit(&o_full[s]);
         if (im.issue) umma_commit(&v_empty[s]);
         im.sync();
         if (k + 2 < K) issue_s(k + 2);                // S buffer s is free: p_full(k) has been seen
@@ -265,32 +281,41 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
 #pragma unroll
     for (int d = 0; d < 16; ++d) o_rem[d] = 0.f;
 
-    // scores of step k -> running max / partial sum, P(k) (bf16) into buffer k & 1; returns alpha(k)
-    auto softmax_step = [&](int k) -> float {
-      const int it = k / T, j = k - it * T, s = k & 1;
-      int n, h, i;
-      decode(it, n, h, i);
-      int hi = min(Rt, L - j * Rt);                                   // valid keys [0, hi) of this tile
-      if (CAUSAL) hi = min(hi, i * Rt + row - j * Rt + 1);
+    // scores of step k (cursor c) -> running max / partial sum, P(k) (bf16) into buffer k & 1; returns alpha(k)
+    auto softmax_step = [&](int k, const StepCursor& c) -> float {
+      const int s = k & 1;
+      int hi = min(Rt, L - c.j * Rt);                                 // valid keys [0, hi) of this tile
+      if (CAUSAL) hi = min(hi, c.i * Rt + row - c.j * Rt + 1);
+      const bool need_mask = CAUSAL || hi < c_end;                    // warp-uniform without the causal mask
       mbar_wait(&s_full[s], (k >> 1) & 1);
       tc_fence_after();
       float alpha = 0.f;
       if (active) {
         uint32_t v[3][16];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          if (c_begin + 16 * c < c_end) tmem_ld_32x16(t_row + s * 128 + c_begin + 16 * c, v[c]);
+        for (int c3 = 0; c3 < 3; ++c3)
+          if (c_begin + 16 * c3 < c_end) tmem_ld_32x16(t_row + s * 128 + c_begin + 16 * c3, v[c3]);
         tmem_ld_wait();
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (need_mask) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (c_begin + 16 * c < c_end) {
+          for (int c3 = 0; c3 < 3; ++c3) {
+            if (c_begin + 16 * c3 < c_end) {
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              float x = __uint_as_float(v[c][jj]);
-              if (c_begin + 16 * c + jj >= hi) x = -INFINITY;
-              v[c][jj] = __float_as_uint(x);
-              mx[jj & 3] = fmaxf(mx[jj & 3], x);
+              for (int jj = 0; jj < 16; ++jj) {
+                float x = __uint_as_float(v[c3][jj]);
+                if (c_begin + 16 * c3 + jj >= hi) x = -INFINITY;
+                v[c3][jj] = __float_as_uint(x);
+                mx[jj & 3] = fmaxf(mx[jj & 3], x);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c3 = 0; c3 < 3; ++c3) {
+            if (c_begin + 16 * c3 < c_end) {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) mx[jj & 3] = fmaxf(mx[jj & 3], __uint_as_float(v[c3][jj]));
             }
           }
         }
@@ -305,17 +330,17 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
         float sm[4] = {0.f, 0.f, 0.f, 0.f};
         uint8_t* pbuf = smem + Sm::kPOff + s * kTcPBytes;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (c_begin + 16 * c < c_end) {
+        for (int c3 = 0; c3 < 3; ++c3) {
+          if (c_begin + 16 * c3 < c_end) {
             float pr[16];
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
-              pr[jj] = ex2_approx(fmaf(__uint_as_float(v[c][jj]), p.scale_log2, -ms));   // exp2(-inf) = 0
+              pr[jj] = ex2_approx(fmaf(__uint_as_float(v[c3][jj]), p.scale_log2, -ms));   // exp2(-inf) = 0
               sm[jj & 3] += pr[jj];
             }
 #pragma unroll
             for (int g8 = 0; g8 < 2; ++g8)
-              *reinterpret_cast<uint4*>(pbuf + p_tile_off(row, ((c_begin + 16 * c) >> 3) + g8)) = pack8_bf16(pr + 8 * g8);
+              *reinterpret_cast<uint4*>(pbuf + p_tile_off(row, ((c_begin + 16 * c3) >> 3) + g8)) = pack8_bf16(pr + 8 * g8);
           }
         }
         l = fmaf(l, alpha, (sm[0] + sm[1]) + (sm[2] + sm[3]));
@@ -327,25 +352,33 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
       return alpha;
     };
 
+    StepCursor cn, co;      // cn: the step the softmax works on (one ahead), co: the step whose O_j is read
+    cn.init(T); co.init(T);
+    if (K > 0) decode(0, cn.n, cn.h, cn.i);
+    co.n = cn.n; co.h = cn.h; co.i = cn.i;
     float alpha_cur = 0.f, alpha_next = 0.f;
-    if (K > 0) alpha_cur = softmax_step(0);
+    if (K > 0) {
+      alpha_cur = softmax_step(0, cn);
+      if (cn.advance() && cn.it < n_local) decode(cn.it, cn.n, cn.h, cn.i);
+    }
     for (int k = 0; k < K; ++k) {
-      const int it = k / T, j = k - it * T;
-      const bool last = j == T - 1;
+      const bool last = co.j == T - 1;
       const float l_fin = l, ms_fin = ms;      // state of step k's item before the next step touches it
       if (k + 1 < K) {
         if (last) { m = -INFINITY; ms = 0.f; l = 0.f; }   // step k+1 opens the next item
-        alpha_next = softmax_step(k + 1);
+        alpha_next = softmax_step(k + 1, cn);
+        if (cn.advance() && cn.it < n_local) decode(cn.it, cn.n, cn.h, cn.i);
       }
       // ---- O_j (fresh accumulator of key tile j) -> running output row in registers
-      mbar_wait(o_full, k & 1);
+      mbar_wait(&o_full[k & 1], (k >> 1) & 1);
       tc_fence_after();
       if (active) {
+        const uint32_t t_o = t_row + kColO + (k & 1) * 128;
         uint32_t t[32];
-        tmem_ld_32x32(t_row + kColO + half * 32, t);
+        tmem_ld_32x32(t_o + half * 32, t);
         if (Tl::kRem != 0 && half == 0) {
           uint32_t t2[16];
-          tmem_ld_32x16(t_row + kColO + 64, t2);
+          tmem_ld_32x16(t_o + 64, t2);
           tmem_ld_wait();
 #pragma unroll
           for (int d = 0; d < 16; ++d) o_rem[d] = fmaf(o_rem[d], alpha_cur, __uint_as_float(t2[d]));
@@ -357,10 +390,9 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(o_read);
+      if (lane == 0) mbar_arrive(&o_read[k & 1]);
       if (last && active) {
-        int n, h, i;
-        decode(it, n, h, i);
+        const int n = co.n, h = co.h, i = co.i;
         xsum[half * 128 + row] = l_fin;
         pair_sync(q);
         const float lt = l_fin + xsum[(half ^ 1) * 128 + row];
@@ -387,6 +419,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
         for (int d = 0; d < 16; ++d) o_rem[d] = 0.f;
       }
       alpha_cur = alpha_next;
+      if (co.advance() && co.it < n_local) decode(co.it, co.n, co.h, co.i);
     }
   }
 
@@ -469,14 +502,15 @@ struct FlashTile96 {
   static constexpr uint32_t kRowBytes = 2 * HD;
 };
 
-template <int HD>
+template <int HD, bool PIPE>
 struct FlashBwdSmem {
   using Tl = FlashTile96<HD>;
   static constexpr int kPAtom = kFbRows * 128;                 // one 64-key atom of P or dS
-  static constexpr int kPOff = 0;
-  static constexpr int kDsOff = 2 * kPAtom;
-  static constexpr int kKvOff = 4 * kPAtom;                    // 2 slots x {K, V}
-  static constexpr int kQdOff = kKvOff + 4 * Tl::kOpBytes;     // 2 slots x {Q, dO, O}
+  static constexpr int kPdsBytes = 4 * kPAtom;                 // one {P, dS} buffer: 2 x 2 atoms
+  static constexpr int kNumPds = PIPE ? 2 : 1;
+  static constexpr int kPdsOff = 0;                            // {P, dS} buffers first: the M = 128 over-read of the
+  static constexpr int kKvOff = kNumPds * kPdsBytes;           //   last dS atom lands in the operand slots below
+  static constexpr int kQdOff = kKvOff + 4 * Tl::kOpBytes;     // 2 slots x {K, V}, then 2 slots x {Q, dO, O}
   static constexpr int kBarOff = kQdOff + 6 * Tl::kOpBytes;
   static constexpr int kTotal = kBarOff + 256 + 1024;
   static_assert(kTotal <= 227 * 1024, "flash attention backward shared memory budget");
@@ -511,30 +545,48 @@ __device__ __forceinline__ uint32_t fb_tile_off(int row, int chunk) {
   return (chunk >> 3) * (kFbRows * 128) + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
 }
 
-template <int HD, bool CAUSAL>
+// (item, key tile j, query tile i) position of a backward step, i fastest
+struct BwdCursor {
+  int it, j, i, T;
+  int n, h;        // decoded item
+  __device__ __forceinline__ void init(int tiles) { it = 0; j = 0; i = 0; T = tiles; n = h = 0; }
+  __device__ __forceinline__ bool advance() {   // true when it moved on to the next item
+    if (++i == T) {
+      i = 0;
+      if (++j == T) { j = 0; ++it; return true; }
+    }
+    return false;
+  }
+};
+
+// PIPE (head_dim 64: two {P, dS} buffers fit): the worker loop is skewed by one step like
+// attn_bwd_tc_pipe_kernel -- scores stage of step k+1 runs while the tensor pipe does the gradient MMAs of
+// step k, and S/dP(k+1) are issued right behind pds_full(k):
+//     workers:  ... | P/dS(k+1) from S/dP(k+1) | epilogue(k) | P/dS(k+2) | epilogue(k+1) | ...
+//     tensor :  ... | S,dP(k+2) | dV,dK,dQ(k+1) | S,dP(k+3) | dV,dK,dQ(k+2) | ...
+// (unpipelined, the workers spent 32 % of their samples waiting for the gradient MMAs: ncu source view, r02).
+template <int HD, bool CAUSAL, bool PIPE>
 __global__ void __launch_bounds__(kFlThreads, 1)
 attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_constant__ CUtensorMap tq_rem,
                       const __grid_constant__ CUtensorMap td_main, const __grid_constant__ CUtensorMap td_rem,
                       const __grid_constant__ CUtensorMap to_main, const __grid_constant__ CUtensorMap to_rem,
                       const FlashBwdParams p) {
   using Tl = FlashTile96<HD>;
-  using Sm = FlashBwdSmem<HD>;
+  using Sm = FlashBwdSmem<HD, PIPE>;
   constexpr int kPAtom = Sm::kPAtom;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* p_buf = smem + Sm::kPOff;
-  uint8_t* ds_buf = smem + Sm::kDsOff;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Sm::kBarOff);
   uint64_t* kv_full = bars;           // [2] K_j, V_j landed
   uint64_t* kv_empty = bars + 2;      // [2] last gradient MMA that reads K_j done
   uint64_t* qd_full = bars + 4;       // [2] Q_i, dO_i, O_i landed
   uint64_t* qd_empty = bars + 6;      // [2] gradient MMAs of the step done
   uint64_t* sdp_full = bars + 8;      // S and dP in TMEM
-  uint64_t* pds_full = bars + 9;      // P and dS in smem (8 warp arrivals)
-  uint64_t* grad_full = bars + 10;    // dQ (and dK, dV) in TMEM
-  uint64_t* t_free = bars + 11;       // gradients read out (8 warp arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* pds_full = bars + 9;      // [2] P and dS buffer written (8 warp arrivals)
+  uint64_t* grad_full = bars + 11;    // dQ (and dK, dV) in TMEM
+  uint64_t* t_free = bars + 12;       // gradients read out (8 warp arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L, H = p.H, D = H * HD, T = p.T, Rt = p.Rt;
@@ -553,9 +605,9 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
       mbar_init(&kv_empty[i], 1);
       mbar_init(&qd_full[i], 1);
       mbar_init(&qd_empty[i], 1);
+      mbar_init(&pds_full[i], 8);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 8);
     mbar_init(grad_full, 1);
     mbar_init(t_free, 8);
     fence_mbar_init();
@@ -568,30 +620,40 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
   constexpr uint32_t kColS = 0, kColDp = 128, kColDq = 256, kColDk = 256 + HD, kColDv = 256 + 2 * HD;
 
   const int n_local = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int TT = T * T;
-  const int K = n_local * TT;      // steps: (item, key tile j, query tile i), i fastest
+  const int K = n_local * T * T;   // steps: (item, key tile j, query tile i), i fastest
+  auto decode = [&](BwdCursor& c) {
+    const int prob = blockIdx.x + c.it * gridDim.x;
+    c.n = prob / H;
+    c.h = prob - c.n * H;
+  };
+  // {P, dS} buffer and its barrier for step k
+  auto pds_buf = [&](int k) -> int { return PIPE ? (k & 1) : 0; };
+  auto pds_par = [&](int k) -> uint32_t { return PIPE ? ((k >> 1) & 1) : (k & 1); };
 
   if (warp == 0) {
     if (lane == 0) {
+      BwdCursor c;
+      c.init(T);
+      decode(c);
+      int jj = 0;      // running (item, key tile) count
       for (int k = 0; k < K; ++k) {
-        const int it = k / TT, r = k - it * TT, j = r / T, i = r - j * T;
-        const int prob = blockIdx.x + it * gridDim.x;
-        const int n = prob / H, h = prob - n * H;
-        if (i == 0) {
-          const int jj = it * T + j, s = jj & 1;
+        if (c.i == 0) {
+          const int s = jj & 1;
           mbar_wait(&kv_empty[s], ((jj >> 1) & 1) ^ 1);
           uint8_t* st = smem + Sm::kKvOff + s * 2 * Tl::kOpBytes;
           mbar_expect_tx(&kv_full[s], 2u * (uint32_t)Rt * Tl::kRowBytes);
-          flash96_load_op<HD>(st, &tq_main, &tq_rem, &kv_full[s], D + h * HD, n * L + j * Rt);
-          flash96_load_op<HD>(st + Tl::kOpBytes, &tq_main, &tq_rem, &kv_full[s], 2 * D + h * HD, n * L + j * Rt);
+          flash96_load_op<HD>(st, &tq_main, &tq_rem, &kv_full[s], D + c.h * HD, c.n * L + c.j * Rt);
+          flash96_load_op<HD>(st + Tl::kOpBytes, &tq_main, &tq_rem, &kv_full[s], 2 * D + c.h * HD, c.n * L + c.j * Rt);
+          ++jj;
         }
         const int s = k & 1;
         mbar_wait(&qd_empty[s], ((k >> 1) & 1) ^ 1);
         uint8_t* st = smem + Sm::kQdOff + s * 3 * Tl::kOpBytes;
         mbar_expect_tx(&qd_full[s], 3u * (uint32_t)Rt * Tl::kRowBytes);
-        flash96_load_op<HD>(st, &tq_main, &tq_rem, &qd_full[s], h * HD, n * L + i * Rt);
-        flash96_load_op<HD>(st + Tl::kOpBytes, &td_main, &td_rem, &qd_full[s], h * HD, n * L + i * Rt);
-        flash96_load_op<HD>(st + 2 * Tl::kOpBytes, &to_main, &to_rem, &qd_full[s], h * HD, n * L + i * Rt);
+        flash96_load_op<HD>(st, &tq_main, &tq_rem, &qd_full[s], c.h * HD, c.n * L + c.i * Rt);
+        flash96_load_op<HD>(st + Tl::kOpBytes, &td_main, &td_rem, &qd_full[s], c.h * HD, c.n * L + c.i * Rt);
+        flash96_load_op<HD>(st + 2 * Tl::kOpBytes, &to_main, &to_rem, &qd_full[s], c.h * HD, c.n * L + c.i * Rt);
+        if (c.advance() && c.it < n_local) decode(c);
       }
     }
   } else if (warp == 1) {
@@ -603,11 +665,14 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
       const uint32_t idesc_q64 = make_idesc_bf16(128, 64, false, true);                // A K (dS), B MN (K)
       const uint32_t idesc_q16 = make_idesc_bf16(128, 16, false, true);
       const int ksteps = p.npad / 16;
-      auto issue_scores = [&](int k) {
-        const int it = k / TT, r = k - it * TT, j = r / T, i = r - j * T;
-        const int jj = it * T + j, sk = jj & 1, s = k & 1;
+      BwdCursor cs, cg;     // cs: next scores step to issue, cg: gradient step
+      cs.init(T); cg.init(T);
+      int jj_s = 0, jj_g = 0;   // key-tile counters of the two cursors ((item, j) pairs started so far)
+      auto issue_scores = [&](int k) {      // k == cs's step
+        if (cs.i == 0) ++jj_s;
+        const int sk = (jj_s - 1) & 1, s = k & 1;
         mbar_wait(&qd_full[s], (k >> 1) & 1);
-        if (i == 0) mbar_wait(&kv_full[sk], (jj >> 1) & 1);
+        if (cs.i == 0) mbar_wait(&kv_full[sk], ((jj_s - 1) >> 1) & 1);
         tc_fence_after();
         const uint32_t qa = smem_u32(smem + Sm::kQdOff + s * 3 * Tl::kOpBytes);
         const uint32_t doa = qa + Tl::kOpBytes;
@@ -617,19 +682,16 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
         flash96_mma_kmajor<HD>(tmem_base + kColDp, doa, va, idesc_s, im.issue);
         if (im.issue) umma_commit(sdp_full);
         im.sync();
+        cs.advance();
       };
-      if (K > 0) issue_scores(0);
-      for (int k = 0; k < K; ++k) {
-        const int it = k / TT, r = k - it * TT, j = r / T, i = r - j * T;
-        const int jj = it * T + j, sk = jj & 1, s = k & 1;
-        mbar_wait(pds_full, k & 1);         // P/dS(k) in smem; S/dP(k) consumed
-        mbar_wait(t_free, (k & 1) ^ 1);     // gradients of step k-1 read out of TMEM
-        tc_fence_after();
+      auto issue_grads = [&](int k) {       // k == cg's step
+        if (cg.i == 0) ++jj_g;
+        const int sk = (jj_g - 1) & 1, s = k & 1;
         const uint32_t qa = smem_u32(smem + Sm::kQdOff + s * 3 * Tl::kOpBytes);
         const uint32_t doa = qa + Tl::kOpBytes;
         const uint32_t ka = smem_u32(smem + Sm::kKvOff + sk * 2 * Tl::kOpBytes);
-        const uint32_t pa = smem_u32(p_buf), dsa = smem_u32(ds_buf);
-        const uint32_t acc0 = i > 0 ? 1u : 0u;   // dK_j, dV_j accumulate over the query tiles
+        const uint32_t pa = smem_u32(smem + Sm::kPdsOff + pds_buf(k) * Sm::kPdsBytes), dsa = pa + 2 * kPAtom;
+        const uint32_t acc0 = cg.i > 0 ? 1u : 0u;   // dK_j, dV_j accumulate over the query tiles
         for (int kk = 0; kk < ksteps; ++kk) {
           // contraction over queries: A = P^T / dS^T (MN-major view of the [query][key] tiles: key atoms
           // one atom apart = LBO, 8-query groups 1 KB apart = SBO), B = dO / Q consumed MN-major
@@ -656,15 +718,25 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
         }
         if (im.issue) umma_commit(grad_full);
         if (im.issue) umma_commit(&qd_empty[s]);
-        if (i == T - 1 && im.issue) umma_commit(&kv_empty[sk]);
+        if (cg.i == T - 1 && im.issue) umma_commit(&kv_empty[sk]);
         im.sync();
-        if (k + 1 < K) issue_scores(k + 1);
+        cg.advance();
+      };
+      if (K > 0) issue_scores(0);
+      for (int k = 0; k < K; ++k) {
+        mbar_wait(&pds_full[pds_buf(k)], pds_par(k));   // P/dS(k) in smem; S/dP(k) consumed
+        tc_fence_after();
+        if (PIPE && k + 1 < K) issue_scores(k + 1);     // under the workers' epilogue of step k-1
+        mbar_wait(t_free, (k & 1) ^ 1);                 // gradients of step k-1 read out of TMEM
+        tc_fence_after();
+        issue_grads(k);
+        if (!PIPE && k + 1 < K) issue_scores(k + 1);
       }
     }
   } else {
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int row = q * 32 + lane;          // query index (elementwise stage, dQ rows) / key index (dK, dV rows)
+    const int row = q * 32 + lane;          // query index (scores stage, dQ rows) / key index (dK, dV rows)
     const bool warp_writes = q * 32 < p.npad;
     const bool warp_stores = q * 32 < Rt;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -673,13 +745,10 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
     const int c_begin = half * hsplit;
     const int c_end = min(p.npad, c_begin + hsplit);
     float* scr = p.scratch + (long long)blockIdx.x * T * Rt * HD;
-    auto lse_of = [&](int k) -> float {     // lse is [batch, H, L]
-      const int it = k / TT, r = k - it * TT, i = r % T;
-      const int prob = blockIdx.x + it * gridDim.x;
-      const int qi = i * Rt + row;
-      return (row < Rt && qi < L) ? p.lse[(long long)prob * L + qi] : 0.f;
+    auto lse_of = [&](const BwdCursor& c) -> float {     // lse is [batch, H, L]
+      const int qi = c.i * Rt + row;
+      return (row < Rt && qi < L) ? p.lse[((long long)c.n * H + c.h) * L + qi] : 0.f;
     };
-    float lse_raw = K > 0 ? lse_of(0) : 0.f;
 
     // 32 (or 16) fp32 columns of this thread's TMEM row at column `col` -> bf16 at dst
     auto store32 = [&](__nv_bfloat16* dst, uint32_t col, bool ok) {
@@ -707,15 +776,20 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
       }
     };
 
-    for (int k = 0; k < K; ++k) {
-      const int it = k / TT, r = k - it * TT, j = r / T, i = r - j * T;
+    BwdCursor cs, ce, cl;      // cs: scores stage, ce: epilogue, cl: one step ahead of cs (lse prefetch)
+    cs.init(T); ce.init(T); cl.init(T);
+    decode(cs);
+    ce.n = cl.n = cs.n; ce.h = cl.h = cs.h;
+    float lse_raw = K > 0 ? lse_of(cl) : 0.f;
+    if (cl.advance() && cl.it < n_local) decode(cl);
+
+    // scores stage of step k (cursor cs): S/dP (TMEM) -> P/dS (bf16, swizzled smem buffer)
+    auto scores_stage = [&](int k) {
       const int s = k & 1;
-      const int prob = blockIdx.x + it * gridDim.x;
-      const int n = prob / H, h = prob - n * H;
-      const int qvalid = min(Rt, L - i * Rt), kvalid = min(Rt, L - j * Rt);
+      const int qvalid = min(Rt, L - cs.i * Rt), kvalid = min(Rt, L - cs.j * Rt);
       const bool row_ok = row < qvalid;
       int hi = kvalid;
-      if (CAUSAL) hi = min(hi, i * Rt + row - j * Rt + 1);
+      if (CAUSAL) hi = min(hi, cs.i * Rt + row - cs.j * Rt + 1);
       // delta_i = sum_d dO_id * O_id from the swizzled smem tiles (same swizzle in both tiles, so any
       // consistent chunk order gives matching pairs)
       mbar_wait(&qd_full[s], (k >> 1) & 1);
@@ -732,19 +806,30 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
           d4[2] = fmaf(bf16lo(a.z), bf16lo(b.z), fmaf(bf16hi(a.z), bf16hi(b.z), d4[2]));
           d4[3] = fmaf(bf16lo(a.w), bf16lo(b.w), fmaf(bf16hi(a.w), bf16hi(b.w), d4[3]));
         };
+        // lanes read the 16-byte chunks of their row in the swizzle's rotated order: conflict-free
+        // (the plain order put 8 lanes of a quarter-warp phase on the same 4 banks: 8-way conflicts)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc16(ot + row * 128 + (c << 4), dot + row * 128 + (c << 4));
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+          acc16(ot + off, dot + off);
+        }
         if constexpr (HD != 64) {
-          acc16(ot + Tl::kMainBytes + row * 32, dot + Tl::kMainBytes + row * 32);
-          acc16(ot + Tl::kMainBytes + row * 32 + 16, dot + Tl::kMainBytes + row * 32 + 16);
+          const uint32_t o0 = Tl::kMainBytes + row * 32 + (((row >> 2) & 1) << 4);
+          acc16(ot + o0, dot + o0);
+          acc16(ot + (o0 ^ 16), dot + (o0 ^ 16));
         }
         delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
       }
       mbar_wait(sdp_full, k & 1);
       tc_fence_after();
       const float lse2 = lse_raw * 1.4426950408889634f;
-      if (k + 1 < K) lse_raw = lse_of(k + 1);     // consumed one whole step later
+      if (k + 1 < K) {                       // next step's lse: consumed one whole stage later
+        lse_raw = lse_of(cl);
+        if (cl.advance() && cl.it < n_local) decode(cl);
+      }
       if (warp_writes) {
+        uint8_t* p_buf = smem + Sm::kPdsOff + pds_buf(k) * Sm::kPdsBytes;
+        uint8_t* ds_buf = p_buf + 2 * kPAtom;
         for (int c = c_begin; c < c_end; c += 16) {
           uint32_t sv[16], dv[16];
           tmem_ld_32x16(t_row + kColS + c, sv);
@@ -769,11 +854,16 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
+      if (lane == 0) mbar_arrive(&pds_full[pds_buf(k)]);
+      if (cs.advance() && cs.it < n_local) decode(cs);
+    };
 
-      // ---- epilogue.  dQ: this thread owns columns [32*half, 32*half+32) (+ [64, 80) for half 0) of query
-      // row i*Rt + row; partial sums over the key tiles go through the CTA-private scratch.
+    // epilogue of step k (cursor ce).  dQ: this thread owns columns [32*half, 32*half+32) (+ [64, 80) for
+    // half 0) of query row i*Rt + row; partial sums over the key tiles go through the CTA-private scratch.
+    auto epilogue = [&](int k) {
+      const int n = ce.n, h = ce.h, i = ce.i, j = ce.j;
       const bool first_j = j == 0, last_j = j == T - 1;
+      const bool row_ok = row < min(Rt, L - i * Rt);
       float* srow = scr + (long long)(i * Rt + row) * HD;
       float acc[32], acc2[16];
       const bool dq_ok = warp_stores && row_ok;
@@ -828,7 +918,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
           }
         }
         if (i == T - 1) {                          // dK_j, dV_j complete: rows = keys of tile j
-          const bool k_ok = row < kvalid;
+          const bool k_ok = row < min(Rt, L - j * Rt);
           __nv_bfloat16* krow = p.dqkv + ((long long)n * L + j * Rt + row) * pitch + D + h * HD;
           store32(krow + half * 32, kColDk + half * 32, k_ok);
           store32(krow + D + half * 32, kColDv + half * 32, k_ok);
@@ -841,6 +931,20 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_free);
+      if (ce.advance() && ce.it < n_local) decode(ce);
+    };
+
+    if constexpr (PIPE) {
+      if (K > 0) scores_stage(0);
+      for (int k = 0; k < K; ++k) {
+        if (k + 1 < K) scores_stage(k + 1);
+        epilogue(k);
+      }
+    } else {
+      for (int k = 0; k < K; ++k) {
+        scores_stage(k);
+        epilogue(k);
+      }
     }
   }
 
@@ -878,13 +982,14 @@ static int launch_bwd_flash(const void* qkv, const void* out, const void* dout, 
   if (rc) return rc;
   rc = flash_tmaps<HD>(&to, &tor, out, D, (long long)batch * L, p.Rt);
   if (rc) return rc;
-  constexpr int smem_bytes = FlashBwdSmem<HD>::kTotal;
+  constexpr bool kPipe = HD == 64;      // two {P, dS} buffers only fit next to head_dim-64 operand tiles
+  constexpr int smem_bytes = FlashBwdSmem<HD, kPipe>::kTotal;
   auto launch = [&](auto kern) -> int {
     CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     kern<<<grid, kFlThreads, smem_bytes, stream>>>(tq, tqr, td, tdr, to, tor, p);
     return CLIPA_OK;
   };
-  rc = causal ? launch(attn_bwd_flash_kernel<HD, true>) : launch(attn_bwd_flash_kernel<HD, false>);
+  rc = causal ? launch(attn_bwd_flash_kernel<HD, true, kPipe>) : launch(attn_bwd_flash_kernel<HD, false, kPipe>);
   if (rc) return rc;
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -50,8 +50,8 @@ extern "C" int64_t clipa_clip_lse_workspace(int32_t b_local, int32_t b_global) {
 }
 
 extern "C" int clipa_clip_lse(const void* a, const void* b_all, int32_t b_local, int32_t b_global,
-                              int32_t E, float scale, int32_t label_offset, float* lse, float* diag,
-                              float* workspace, void* stream) {
+                              int32_t E, float scale, const float* scale_dev, int32_t label_offset, float* lse,
+                              float* diag, float* workspace, void* stream) {
   CLIPA_REQUIRE(a && b_all && lse && diag && workspace, CLIPA_ERR_BAD_ARG, "clip_lse: null pointer");
   CLIPA_REQUIRE(b_local > 0 && b_global > 0 && E > 0 && E % 8 == 0, CLIPA_ERR_UNSUPPORTED,
                 "clip_lse: need E %% 8 == 0 (b_local=%d b_global=%d E=%d)", b_local, b_global, E);
@@ -65,6 +65,7 @@ extern "C" int clipa_clip_lse(const void* a, const void* b_all, int32_t b_local,
   p.n_per_chunk = c.n_per_chunk;
   p.split_k = 1;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.scale_dev = scale_dev;
   p.label_offset = label_offset;
   p.part_max = workspace;
   p.part_sum = workspace + (size_t)slots * b_local;
@@ -79,9 +80,9 @@ extern "C" int clipa_clip_lse(const void* a, const void* b_all, int32_t b_local,
 }
 
 extern "C" int clipa_clip_softmax_grad(const void* a, const void* b_all, int32_t b_local,
-                                       int32_t b_global, int32_t E, float scale,
-                                       int32_t label_offset, const float* lse, void* pt,
-                                       int64_t ldpt, float* dscale_partial, void* stream) {
+                                       int32_t b_global, int32_t E, float scale, const float* scale_dev,
+                                       int32_t scale_output, int32_t label_offset, const float* lse,
+                                       void* pt, int64_t ldpt, float* dscale_partial, void* stream) {
   CLIPA_REQUIRE(a && b_all && lse && pt && dscale_partial, CLIPA_ERR_BAD_ARG,
                 "clip_softmax_grad: null pointer");
   CLIPA_REQUIRE(b_local > 0 && b_global > 0 && E > 0 && E % 8 == 0 && ldpt % 8 == 0 &&
@@ -93,6 +94,8 @@ extern "C" int clipa_clip_softmax_grad(const void* a, const void* b_all, int32_t
   p.split_k = 1;
   p.C = pt; p.ldc = ldpt;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.scale_dev = scale_dev;
+  p.scale_out = scale_output;
   p.label_offset = label_offset;
   p.lse = lse;
   p.dscale = dscale_partial;

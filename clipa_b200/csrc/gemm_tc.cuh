@@ -54,6 +54,8 @@ struct GemmParams {
   float* part_sum;     // [n_chunks, M]
   float* diag;         // [M] label logit, natural units
   float* dscale;       // scalar accumulator (SOFTMAX_GRAD)
+  const float* scale_dev;  // if set: logit_scale is read from device memory (no host round trip), scale_log2 ignored
+  int scale_out;           // SOFTMAX_GRAD: store scale * Pt (the gradient GEMMs then need no scale factor)
 };
 
 template <int BN>
@@ -603,6 +605,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       st.m = -INFINITY; st.l = 0.f; st.d = 0.f; st.found = 0;
       float lse2_row = 0.f;
       float ds_acc = 0.f;
+      float scale_log2 = p.scale_log2, out_mul = 1.f;
+      if constexpr (EPI >= EPI_LSE) {
+        if (p.scale_dev) scale_log2 = __ldg(p.scale_dev) * 1.4426950408889634f;
+        if (p.scale_out) out_mul = scale_log2 * 0.69314718055994531f;
+      }
       if constexpr (EPI == EPI_SOFTMAX_GRAD) lse2_row = row_ok ? p.lse[row] * 1.4426950408889634f : 0.f;
       const int label = row + p.label_offset;
 
@@ -639,7 +646,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             float gmax = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              f[j] = (full || col0 + j < p.N) ? f[j] * p.scale_log2 : -INFINITY;
+              f[j] = (full || col0 + j < p.N) ? f[j] * scale_log2 : -INFINITY;
               gmax = fmaxf(gmax, f[j]);
             }
             const float m_new = fmaxf(st.m, gmax);
@@ -658,10 +665,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (row_ok) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float pt = exp2f(f[j] * p.scale_log2 - lse2_row) - ((col0 + j == label) ? 1.f : 0.f);
+                const float pt = exp2f(f[j] * scale_log2 - lse2_row) - ((col0 + j == label) ? 1.f : 0.f);
                 const bool ok = full || (col0 + j < p.N);
                 ds_acc += ok ? pt * f[j] : 0.f;
-                f[j] = pt;
+                f[j] = pt * out_mul;
               }
               __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
               if (full) store_bf16x32(dst, f);

@@ -247,35 +247,42 @@ class ClipLossFn(torch.autograd.Function):
                 need_all_grads):
         bl, E = image_features.shape
         bg = all_image.shape[0]
-        s = float(logit_scale)
         off = rank * bl if bg != bl else 0
         dev = image_features.device
+        # the (exponentiated) logit scale stays on the device: the head kernels read it through a pointer,
+        # so the step never drains the launch queue between the towers and the head
+        s_dev = logit_scale.detach().to(torch.float32).reshape(1).contiguous()
         img, txt = image_features.contiguous(), text_features.contiguous()
         aimg, atxt = all_image.contiguous(), all_text.contiguous()
-        lse_i, diag_i = ops.clip_lse(img, atxt, s, off)
-        lse_t, diag_t = ops.clip_lse(txt, aimg, s, off)
+        lse_i, diag_i = ops.clip_lse(img, atxt, s_dev, off)
+        lse_t, diag_t = ops.clip_lse(txt, aimg, s_dev, off)
         loss = 0.5 * ((lse_i - diag_i).mean() + (lse_t - diag_t).mean())
-        # gradients (scaled by grad_output in backward)
+        ctx.has_grads = any(ctx.needs_input_grad[:5])
+        if not ctx.has_grads:          # eval / torch.no_grad(): no backward will follow
+            return loss
+        # gradients (scaled by grad_output in backward); P~ tiles are stored pre-multiplied by the scale
         ds = torch.zeros(1, dtype=torch.float32, device=dev)
         c = 0.5 / bl
-        p_i = ops.clip_softmax_grad(img, atxt, s, off, lse_i, ds)   # [bl, bg] bf16
-        p_t = ops.clip_softmax_grad(txt, aimg, s, off, lse_t, ds)
+        p_i = ops.clip_softmax_grad(img, atxt, s_dev, off, lse_i, ds, scale_output=True)   # s * Pi  [bl, bg] bf16
+        p_t = ops.clip_softmax_grad(txt, aimg, s_dev, off, lse_t, ds, scale_output=True)
         d_img = torch.empty(bl, E, dtype=torch.float32, device=dev)
         d_txt = torch.empty(bl, E, dtype=torch.float32, device=dev)
-        ops.gemm(p_i, atxt.t(), d_img, alpha=c * s)                 # dI = c*s * Pi @ T_all
-        ops.gemm(p_t, aimg.t(), d_txt, alpha=c * s)                 # dT = c*s * Pt @ I_all
+        ops.gemm(p_i, atxt.t(), d_img, alpha=c)                     # dI = c*s * Pi @ T_all
+        ops.gemm(p_t, aimg.t(), d_txt, alpha=c)                     # dT = c*s * Pt @ I_all
         d_all_img = d_all_txt = None
-        if need_all_grads:
+        if need_all_grads and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
             d_all_txt = torch.empty(bg, E, dtype=torch.float32, device=dev)
             d_all_img = torch.empty(bg, E, dtype=torch.float32, device=dev)
-            ops.gemm(p_i.t(), img.t(), d_all_txt, alpha=c * s)      # dT_all = c*s * Pi^T @ I
-            ops.gemm(p_t.t(), txt.t(), d_all_img, alpha=c * s)      # dI_all = c*s * Pt^T @ T
+            ops.gemm(p_i.t(), img.t(), d_all_txt, alpha=c)          # dT_all = c*s * Pi^T @ I
+            ops.gemm(p_t.t(), txt.t(), d_all_img, alpha=c)          # dI_all = c*s * Pt^T @ T
         ctx.save_for_backward(d_img, d_txt, d_all_img, d_all_txt, ds * c)
         ctx.dtypes = (image_features.dtype, logit_scale.dtype)
         return loss
 
     @staticmethod
     def backward(ctx, gout):
+        if not ctx.has_grads:
+            return (None,) * 7
         d_img, d_txt, d_all_img, d_all_txt, ds = ctx.saved_tensors
         fdt, sdt = ctx.dtypes
         g = gout.float()

@@ -23,27 +23,32 @@ from .. import functional as Fn
 
 
 class _AllGatherFeatures(torch.autograd.Function):
-    """all_gather_into_tensor forward; reduce_scatter(SUM) backward (gather_with_grad=True),
-    or no gradient to remote rows (gather_with_grad=False)."""
+    """all_gather_into_tensor forward.  Backward, as in open_clip/loss.py:75-88:
+      gather_with_grad            -> reduce_scatter(SUM) (the transpose of torch.distributed.nn.all_gather);
+      else, not local_loss        -> the local slice only (the reference re-inserts the local features into
+                                     the gathered list so that they keep their gradient, loss.py:84-86);
+      else (local_loss, no grad)  -> nothing: the gathered tensors carry no gradient at all."""
 
     @staticmethod
-    def forward(ctx, x, world_size, with_grad):
+    def forward(ctx, x, world_size, with_grad, local_loss):
         x = x.contiguous()
         out = torch.empty(world_size * x.shape[0], x.shape[1], dtype=x.dtype, device=x.device)
         dist.all_gather_into_tensor(out, x)
-        ctx.with_grad = with_grad
+        ctx.with_grad, ctx.local_loss = with_grad, local_loss
         ctx.rank = dist.get_rank()
         ctx.n = x.shape[0]
         return out
 
     @staticmethod
     def backward(ctx, g):
-        g = g.contiguous()
         if ctx.with_grad:
+            g = g.contiguous()
             out = torch.empty(ctx.n, g.shape[1], dtype=g.dtype, device=g.device)
             dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM)
-            return out, None, None
-        return g[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n].clone(), None, None
+            return out, None, None, None
+        if not ctx.local_loss:
+            return g[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n].clone(), None, None, None
+        return None, None, None, None
 
 
 def gather_features(image_features, text_features, local_loss=False, gather_with_grad=False,
@@ -52,8 +57,8 @@ def gather_features(image_features, text_features, local_loss=False, gather_with
     assert has_distributed, 'torch.distributed did not import correctly'
     if use_horovod:
         raise NotImplementedError("horovod backend is not built (single backend: NCCL via torch.distributed)")
-    all_image = _AllGatherFeatures.apply(image_features, world_size, gather_with_grad)
-    all_text = _AllGatherFeatures.apply(text_features, world_size, gather_with_grad)
+    all_image = _AllGatherFeatures.apply(image_features, world_size, gather_with_grad, local_loss)
+    all_text = _AllGatherFeatures.apply(text_features, world_size, gather_with_grad, local_loss)
     return all_image, all_text
 
 
@@ -79,8 +84,9 @@ class ClipLoss(nn.Module):
                 image_features, text_features, self.local_loss, self.gather_with_grad, self.rank,
                 self.world_size, self.use_horovod)
             if self.local_loss:
+                # without gather_with_grad the gathered tensors are constants here: skip their gradient GEMMs
                 total_loss = Fn.ClipLossFn.apply(image_features, text_features, all_image, all_text,
-                                                 logit_scale, self.rank, True)
+                                                 logit_scale, self.rank, self.gather_with_grad)
             else:
                 # full-matrix form (loss.py:138-139): every rank evaluates all rows
                 total_loss = Fn.ClipLossFn.apply(all_image, all_text, all_image, all_text,

@@ -200,8 +200,17 @@ def colsum_accum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def clip_lse(a: torch.Tensor, b_all: torch.Tensor, scale: float, label_offset: int):
-    """Row log-sum-exp and label logit of scale * a @ b_all^T, logits never materialised."""
+def _scale_args(scale):
+    """(host float, device pointer): a tensor scale stays on the device (no .item() sync)."""
+    if isinstance(scale, torch.Tensor):
+        assert scale.is_cuda and scale.dtype == torch.float32 and scale.numel() == 1
+        return 0.0, _ptr(scale)
+    return float(scale), None
+
+
+def clip_lse(a: torch.Tensor, b_all: torch.Tensor, scale, label_offset: int):
+    """Row log-sum-exp and label logit of scale * a @ b_all^T, logits never materialised.
+    `scale`: python float, or a 1-element fp32 CUDA tensor (read on the device)."""
     assert a.dtype == torch.bfloat16 and b_all.dtype == torch.bfloat16
     assert a.is_contiguous() and b_all.is_contiguous()
     bl, E = a.shape
@@ -210,22 +219,26 @@ def clip_lse(a: torch.Tensor, b_all: torch.Tensor, scale: float, label_offset: i
     ws = torch.empty(nws, dtype=torch.float32, device=a.device)
     lse = torch.empty(bl, dtype=torch.float32, device=a.device)
     diag = torch.empty(bl, dtype=torch.float32, device=a.device)
+    s_host, s_dev = _scale_args(scale)
     with _prof(("clip_lse", bl, bg, E), 2.0 * bl * bg * E, 2.0 * (bl + bg) * E):
-        check(_lib.lib().clipa_clip_lse(_ptr(a), _ptr(b_all), bl, bg, E, scale, label_offset, _ptr(lse),
+        check(_lib.lib().clipa_clip_lse(_ptr(a), _ptr(b_all), bl, bg, E, s_host, s_dev, label_offset, _ptr(lse),
                                         _ptr(diag), _ptr(ws), _stream()), "clipa_clip_lse")
     return lse, diag
 
 
-def clip_softmax_grad(a, b_all, scale: float, label_offset: int, lse: torch.Tensor,
-                      dscale_partial: torch.Tensor):
+def clip_softmax_grad(a, b_all, scale, label_offset: int, lse: torch.Tensor,
+                      dscale_partial: torch.Tensor, scale_output: bool = False):
+    """Pt = softmax(scale * a @ b_all^T) - onehot (bf16 [bl, bg]); with scale_output the stored matrix is
+    scale * Pt, so the gradient GEMMs that consume it need no logit-scale factor from the host."""
     bl, E = a.shape
     bg = b_all.shape[0]
     ld = (bg + 7) // 8 * 8    # row pitch must stay 16-byte aligned for TMA consumers
     pt = torch.empty(bl, ld, dtype=torch.bfloat16, device=a.device)[:, :bg]
+    s_host, s_dev = _scale_args(scale)
     with _prof(("clip_softmax_grad", bl, bg, E), 2.0 * bl * bg * E, 2.0 * (bl + bg) * E + 2.0 * bl * bg):
-        check(_lib.lib().clipa_clip_softmax_grad(_ptr(a), _ptr(b_all), bl, bg, E, scale, label_offset,
-                                                 _ptr(lse), _ptr(pt), pt.stride(0), _ptr(dscale_partial),
-                                                 _stream()), "clipa_clip_softmax_grad")
+        check(_lib.lib().clipa_clip_softmax_grad(_ptr(a), _ptr(b_all), bl, bg, E, s_host, s_dev, int(scale_output),
+                                                 label_offset, _ptr(lse), _ptr(pt), pt.stride(0),
+                                                 _ptr(dscale_partial), _stream()), "clipa_clip_softmax_grad")
     return pt
 
 

@@ -138,15 +138,20 @@ int clipa_colsum_accum(const void* x, int64_t ldx, float* out, int64_t rows, int
  *                           workspace: f32 [2 * n_chunks * B_local], n_chunks from
  *                           clipa_clip_lse_workspace().
  *   clipa_clip_softmax_grad: Pt[i,j] = exp(scale*a_i.b_j - lse_i) - [j == i+label_offset] (bf16
- *                           [B_local, B_global]) and dscale_partial += sum_ij Pt[i,j]*(a_i.b_j).
+ *                           [B_local, B_global]; multiplied by `scale` when scale_output != 0) and
+ *                           dscale_partial += sum_ij Pt[i,j]*(a_i.b_j).
+ * `scale` is the exponentiated logit scale (CLIP.forward returns logit_scale.exp(), model.py:273).  If
+ * `scale_dev` is non-NULL it points to that f32 scalar in DEVICE memory and `scale` is ignored: the
+ * training step then never reads the parameter back to the host.
  * The caller (ClipLoss autograd function) turns these into loss, d a, d b_all via clipa_gemm. */
 int64_t clipa_clip_lse_workspace(int32_t b_local, int32_t b_global);
 int clipa_clip_lse(const void* a, const void* b_all, int32_t b_local, int32_t b_global, int32_t E,
-                   float scale, int32_t label_offset, float* lse, float* diag, float* workspace,
-                   void* stream);
+                   float scale, const float* scale_dev, int32_t label_offset, float* lse, float* diag,
+                   float* workspace, void* stream);
 int clipa_clip_softmax_grad(const void* a, const void* b_all, int32_t b_local, int32_t b_global,
-                            int32_t E, float scale, int32_t label_offset, const float* lse,
-                            void* pt, int64_t ldpt, float* dscale_partial, void* stream);
+                            int32_t E, float scale, const float* scale_dev, int32_t scale_output,
+                            int32_t label_offset, const float* lse, void* pt, int64_t ldpt,
+                            float* dscale_partial, void* stream);
 
 /* ---- fused AdamW step ("next" row 8f.1) -----------------------------------------------------------
  * torch.optim.AdamW as built at training/main.py:318-326 (decoupled weight decay, bias correction),

@@ -63,7 +63,10 @@ def test_null_and_bad_arguments_are_rejected_with_messages(lib):
     assert b"multiples of 8" in lib.clipa_last_error()
     assert lib.clipa_layernorm_fwd(None, None, None, None, None, None, 4, 64, 1e-5, None) == -1
     assert lib.clipa_attention_fwd(None, None, None, 1, 1, 1, 64, 0, None) == -1
-    assert lib.clipa_clip_lse(None, None, 8, 8, 64, 1.0, 0, None, None, None, None) == -1
+    assert lib.clipa_clip_lse(None, None, 8, 8, 64, 1.0, None, 0, None, None, None, None) == -1
+    assert lib.clipa_attention_bwd(None, None, None, None, None, None, 0, 1, 1, 1, 64, 0, None) == -1
+    assert lib.clipa_attention_bwd_workspace(2, 257, 4, 64) >= 2 * 4 * 258 * 64 * 4   # 3 tiles of 86 rows, fp32 dQ partials
+    assert lib.clipa_attention_bwd_workspace(2, 82, 4, 64) == 0
     assert lib.clipa_clip_lse_workspace(4096, 32768) > 0
     assert lib.clipa_launch_count() == 0   # nothing was launched by the rejected calls
 
