@@ -66,7 +66,7 @@ _SIGNATURES = {
                                      C.c_void_p]),
     "clipa_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
-                                   C.c_float, C.c_int32, C.c_void_p]),
+                                   C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
     "clipa_clip_lse_workspace": (C.c_int64, [C.c_int32, C.c_int32]),
     "clipa_clip_lse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -11,7 +11,9 @@ namespace clipa {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
              uint2* __restrict__ p_bf16, long long n4, float lr, float beta1, float beta2, float eps,
-             float decay_factor, float inv_bc1, float inv_sqrt_bc2, float grad_scale, int zero_grad) {
+             float decay_factor, float inv_bc1, float inv_sqrt_bc2, float grad_scale,
+             const float* __restrict__ grad_scale_dev, int zero_grad) {
+  if (grad_scale_dev) grad_scale *= __ldg(grad_scale_dev);   // e.g. the gradient-clipping factor, computed on the device
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
@@ -40,7 +42,8 @@ using namespace clipa;
 
 extern "C" int clipa_adamw_step(void* param, void* grad, void* exp_avg, void* exp_avg_sq, void* param_bf16,
                                 int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                int32_t step, float grad_scale, int32_t zero_grad, void* stream) {
+                                int32_t step, float grad_scale, const float* grad_scale_dev, int32_t zero_grad,
+                                void* stream) {
   CLIPA_REQUIRE(param && grad && exp_avg && exp_avg_sq, CLIPA_ERR_BAD_ARG, "adamw_step: null pointer");
   CLIPA_REQUIRE(n > 0 && n % 4 == 0, CLIPA_ERR_BAD_ARG, "adamw_step: n must be a positive multiple of 4 (got %lld)",
                 (long long)n);
@@ -58,7 +61,7 @@ extern "C" int clipa_adamw_step(void* param, void* grad, void* exp_avg, void* ex
   adamw_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<float4*>(param), static_cast<float4*>(grad), static_cast<float4*>(exp_avg),
       static_cast<float4*>(exp_avg_sq), static_cast<uint2*>(param_bf16), n4, lr, beta1, beta2, eps,
-      1.0f - lr * weight_decay, (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)), grad_scale, zero_grad);
+      1.0f - lr * weight_decay, (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)), grad_scale, grad_scale_dev, zero_grad);
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CLIPA_OK;

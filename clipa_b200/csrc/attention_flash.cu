@@ -3,8 +3,10 @@
 // head_dim 80: every ViT-H/14 tower).  Reference call site: nn.MultiheadAttention inside
 // ResidualAttentionBlock.attention, open_clip/transformer.py:209,234-236.
 //
-// A sequence is cut into T = ceil(L / 96) tiles of Rt = ceil(L / T) rows (257 -> 3 x 86, 577 -> 7 x 83),
-// the same cut for queries and keys.  head_dim 80 = one 128B-swizzled operand tile of 64 columns plus a
+// A sequence is cut into T = ceil(L / R) tiles of Rt = ceil(L / T) rows, the same cut for queries and keys
+// (R = 128 forward, 96 backward: 257 -> 3 x 86; 577 -> 5 x 116 / 7 x 83).  Short sequences (2 L <= R) are PACKED:
+// G = R / L consecutive samples of a head share a tile and the score tile is block-diagonal (ViT-H/14 at 37
+// tokens: 3 samples per forward tile, 2 per backward tile).  head_dim 80 = one 128B-swizzled operand tile of 64 columns plus a
 // 32B-swizzled tile of 16 columns: K-major MMAs take the fifth k-step from the small tile, MN-major
 // operands (V, and in backward dO / Q / K) add one N = 16 MMA next to the N = 64 one.
 //
@@ -25,7 +27,8 @@
 namespace clipa {
 
 constexpr int kFlThreads = 320;
-constexpr int kFlMaxRows = 96;   // rows (queries / keys) per tile: 3 x 32-column score chunks per thread
+constexpr int kFlMaxRowsFwd = 128;  // forward: rows (queries / keys) per tile (full 128-row operand tiles)
+constexpr int kFlMaxRowsBwd = 96;   // backward: 96-row operand tiles (shared-memory budget)
 
 template <int HD>
 struct FlashTile {
@@ -42,8 +45,9 @@ struct FlashParams {
   float* lse;
   int L, H, batch;
   int T;       // tiles per sequence
-  int Rt;      // rows per tile
+  int Rt;      // rows per tile (G * L when several short sequences are packed into one tile)
   int npad;    // ceil16(Rt)
+  int G;       // samples packed per tile (1 unless T == 1 and 2 * L <= tile rows): block-diagonal scores
   float scale_log2;
 };
 
@@ -120,7 +124,8 @@ __device__ __forceinline__ void pair_sync(int q) {
 // so the score tile of step k+1 is already in TMEM when the workers finish step k, and P V of step k
 // runs under the softmax of step k+1.  K_j rides 2 steps ahead of V_j in the TMA stream (its slot is
 // free as soon as S has been computed).
-template <int HD, bool CAUSAL>
+// NCH = 16-column score chunks per thread (3: tiles up to 96 keys, 4: up to 128)
+template <int HD, bool CAUSAL, int NCH>
 __global__ void __launch_bounds__(kFlThreads, 1)
 attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_rem,
                       const FlashParams p) {
@@ -146,7 +151,8 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L, H = p.H, D = H * HD, T = p.T, Rt = p.Rt;
-  const int total = p.batch * H * T;
+  const int G = p.G;
+  const int total = ((p.batch + G - 1) / G) * H * T;
 
   // rows [Rt, 128) of the operand tiles are never written by TMA and are multiplied by exactly-zero
   // probabilities: they must not hold NaN/Inf patterns
@@ -179,14 +185,14 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
 
   const int n_local = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int K = n_local * T;           // steps of this CTA
-  // local item `it` -> (sample n, head h, query tile i); the T query tiles of one (n, h) are consecutive
+  // local item `it` -> (first sample n, head h, query tile i); the T query tiles of one (n, h) are consecutive
   // work items, i.e. run on neighbouring CTAs at the same time (their K/V re-reads hit L2)
   auto decode = [&](int it, int& n, int& h, int& i) {
     const int w = blockIdx.x + it * gridDim.x;
     i = w % T;
     const int nh = w / T;
     h = nh % H;
-    n = nh / H;
+    n = (nh / H) * G;
   };
 
   if (warp == 0) {
@@ -274,6 +280,9 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
     const int hsplit = ((p.npad + 31) >> 5) << 4;                // 96 keys: 48 + 48
     const int c_begin = half * hsplit;
     const int c_end = min(p.npad, c_begin + hsplit);
+    // packed tiles: this row's sample within the tile and its first key column
+    const int psample = G > 1 ? min(row, Rt - 1) / L : 0;
+    const int plo = psample * L;
     float m = -INFINITY, ms = 0.f, l = 0.f;
     float o_main[32], o_rem[16];
 #pragma unroll
@@ -284,27 +293,34 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
     // scores of step k (cursor c) -> running max / partial sum, P(k) (bf16) into buffer k & 1; returns alpha(k)
     auto softmax_step = [&](int k, const StepCursor& c) -> float {
       const int s = k & 1;
-      int hi = min(Rt, L - c.j * Rt);                                 // valid keys [0, hi) of this tile
-      if (CAUSAL) hi = min(hi, c.i * Rt + row - c.j * Rt + 1);
-      const bool need_mask = CAUSAL || hi < c_end;                    // warp-uniform without the causal mask
+      int lo = 0, hi;                                                 // valid keys [lo, hi) of this tile
+      if (G > 1) {
+        lo = plo;
+        hi = CAUSAL ? min(plo + L, row + 1) : plo + L;
+      } else {
+        hi = min(Rt, L - c.j * Rt);
+        if (CAUSAL) hi = min(hi, c.i * Rt + row - c.j * Rt + 1);
+      }
+      const bool need_mask = CAUSAL || G > 1 || hi < c_end;           // warp-uniform
       mbar_wait(&s_full[s], (k >> 1) & 1);
       tc_fence_after();
       float alpha = 0.f;
       if (active) {
-        uint32_t v[3][16];
+        uint32_t v[NCH][16];
 #pragma unroll
-        for (int c3 = 0; c3 < 3; ++c3)
+        for (int c3 = 0; c3 < NCH; ++c3)
           if (c_begin + 16 * c3 < c_end) tmem_ld_32x16(t_row + s * 128 + c_begin + 16 * c3, v[c3]);
         tmem_ld_wait();
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (need_mask) {
 #pragma unroll
-          for (int c3 = 0; c3 < 3; ++c3) {
+          for (int c3 = 0; c3 < NCH; ++c3) {
             if (c_begin + 16 * c3 < c_end) {
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) {
                 float x = __uint_as_float(v[c3][jj]);
-                if (c_begin + 16 * c3 + jj >= hi) x = -INFINITY;
+                const int col = c_begin + 16 * c3 + jj;
+                if (col >= hi || col < lo) x = -INFINITY;
                 v[c3][jj] = __float_as_uint(x);
                 mx[jj & 3] = fmaxf(mx[jj & 3], x);
               }
@@ -312,7 +328,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
           }
         } else {
 #pragma unroll
-          for (int c3 = 0; c3 < 3; ++c3) {
+          for (int c3 = 0; c3 < NCH; ++c3) {
             if (c_begin + 16 * c3 < c_end) {
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) mx[jj & 3] = fmaxf(mx[jj & 3], __uint_as_float(v[c3][jj]));
@@ -330,7 +346,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
         float sm[4] = {0.f, 0.f, 0.f, 0.f};
         uint8_t* pbuf = smem + Sm::kPOff + s * kTcPBytes;
 #pragma unroll
-        for (int c3 = 0; c3 < 3; ++c3) {
+        for (int c3 = 0; c3 < NCH; ++c3) {
           if (c_begin + 16 * c3 < c_end) {
             float pr[16];
 #pragma unroll
@@ -396,7 +412,8 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
         xsum[half * 128 + row] = l_fin;
         pair_sync(q);
         const float lt = l_fin + xsum[(half ^ 1) * 128 + row];
-        if (row < min(Rt, L - i * Rt)) {
+        const bool row_valid = G > 1 ? (row < Rt && n + psample < p.batch) : row < min(Rt, L - i * Rt);
+        if (row_valid) {
           const float inv = lt > 0.f ? 1.f / lt : 0.f;
           const long long grow = (long long)n * L + i * Rt + row;
           __nv_bfloat16* dst = p.out + grow * D + h * HD;
@@ -411,7 +428,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
             for (int g8 = 0; g8 < 2; ++g8) reinterpret_cast<uint4*>(dst + 64)[g8] = pack8_bf16(o_rem + 8 * g8);
           }
           if (half == 0)
-            p.lse[((long long)n * H + h) * L + i * Rt + row] = (ms_fin + log2f(lt)) * 0.69314718055994531f;
+            p.lse[((long long)(n + psample) * H + h) * L + i * Rt + row - plo] = (ms_fin + log2f(lt)) * 0.69314718055994531f;
         }
 #pragma unroll
         for (int d = 0; d < 32; ++d) o_main[d] = 0.f;
@@ -431,9 +448,13 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
   }
 }
 
-static void flash_tiling(int L, int& T, int& Rt, int& npad) {
-  T = (L + kFlMaxRows - 1) / kFlMaxRows;
-  Rt = (L + T - 1) / T;
+// Sequence -> tiles.  Long sequences: T equal tiles of Rt = ceil(L / T) rows.  Short ones (T == 1): G = max_rows / L
+// consecutive samples of a head share one tile (rows of G samples are contiguous in the [batch*L, .] matrices);
+// the score tile is then block-diagonal.
+static void flash_tiling(int L, int max_rows, int& T, int& Rt, int& npad, int& G) {
+  T = (L + max_rows - 1) / max_rows;
+  G = T == 1 ? max_rows / L : 1;
+  Rt = T == 1 ? G * L : (L + T - 1) / T;
   npad = (Rt + 15) & ~15;
 }
 
@@ -456,12 +477,12 @@ static int launch_fwd_flash(const void* qkv, void* out, float* lse, int batch, i
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
   p.L = L; p.H = H; p.batch = batch;
-  flash_tiling(L, p.T, p.Rt, p.npad);
+  flash_tiling(L, kFlMaxRowsFwd, p.T, p.Rt, p.npad, p.G);
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
   CUtensorMap tm_main, tm_rem;
   int rc = flash_tmaps<HD>(&tm_main, &tm_rem, qkv, 3 * D, (long long)batch * L, p.Rt);
   if (rc) return rc;
-  const long long total = (long long)batch * H * p.T;
+  const long long total = (long long)((batch + p.G - 1) / p.G) * H * p.T;
   CLIPA_REQUIRE(total < (1LL << 31), CLIPA_ERR_UNSUPPORTED, "attention_fwd: too many work items");
   int grid = num_sms();
   if (grid > total) grid = (int)total;
@@ -471,7 +492,10 @@ static int launch_fwd_flash(const void* qkv, void* out, float* lse, int batch, i
     kern<<<grid, kFlThreads, smem_bytes, stream>>>(tm_main, tm_rem, p);
     return CLIPA_OK;
   };
-  rc = causal ? launch(attn_fwd_flash_kernel<HD, true>) : launch(attn_fwd_flash_kernel<HD, false>);
+  if (p.npad <= 96)
+    rc = causal ? launch(attn_fwd_flash_kernel<HD, true, 3>) : launch(attn_fwd_flash_kernel<HD, false, 3>);
+  else
+    rc = causal ? launch(attn_fwd_flash_kernel<HD, true, 4>) : launch(attn_fwd_flash_kernel<HD, false, 4>);
   if (rc) return rc;
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -522,6 +546,7 @@ struct FlashBwdParams {
   float* scratch;        // [gridDim.x][T * Rt][HD] fp32 (unused when T == 1)
   int L, H, batch;
   int T, Rt, npad;
+  int G;                 // samples packed per tile (see FlashParams)
   float scale;
 };
 
@@ -590,7 +615,8 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.L, H = p.H, D = H * HD, T = p.T, Rt = p.Rt;
-  const int total = p.batch * H;
+  const int G = p.G;
+  const int total = ((p.batch + G - 1) / G) * H;
   const long long pitch = 3LL * D;
 
   for (int i = threadIdx.x; i < Sm::kBarOff / 16; i += blockDim.x)
@@ -621,10 +647,11 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
 
   const int n_local = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int K = n_local * T * T;   // steps: (item, key tile j, query tile i), i fastest
-  auto decode = [&](BwdCursor& c) {
+  auto decode = [&](BwdCursor& c) {          // c.n = FIRST sample of the tile
     const int prob = blockIdx.x + c.it * gridDim.x;
-    c.n = prob / H;
-    c.h = prob - c.n * H;
+    const int tile = prob / H;
+    c.h = prob - tile * H;
+    c.n = tile * G;
   };
   // {P, dS} buffer and its barrier for step k
   auto pds_buf = [&](int k) -> int { return PIPE ? (k & 1) : 0; };
@@ -745,9 +772,14 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
     const int c_begin = half * hsplit;
     const int c_end = min(p.npad, c_begin + hsplit);
     float* scr = p.scratch + (long long)blockIdx.x * T * Rt * HD;
+    // packed tiles: this row's sample within the tile and its first row / key column
+    const int psample = G > 1 ? min(row, Rt - 1) / L : 0;
+    const int plo = psample * L;
+    auto row_valid = [&](const BwdCursor& c, int tile_idx) -> bool {   // row of query tile i / key tile j
+      return G > 1 ? (row < Rt && c.n + psample < p.batch) : row < min(Rt, L - tile_idx * Rt);
+    };
     auto lse_of = [&](const BwdCursor& c) -> float {     // lse is [batch, H, L]
-      const int qi = c.i * Rt + row;
-      return (row < Rt && qi < L) ? p.lse[((long long)c.n * H + c.h) * L + qi] : 0.f;
+      return row_valid(c, c.i) ? p.lse[((long long)(c.n + psample) * H + c.h) * L + c.i * Rt + row - plo] : 0.f;
     };
 
     // 32 (or 16) fp32 columns of this thread's TMEM row at column `col` -> bf16 at dst
@@ -786,10 +818,15 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
     // scores stage of step k (cursor cs): S/dP (TMEM) -> P/dS (bf16, swizzled smem buffer)
     auto scores_stage = [&](int k) {
       const int s = k & 1;
-      const int qvalid = min(Rt, L - cs.i * Rt), kvalid = min(Rt, L - cs.j * Rt);
-      const bool row_ok = row < qvalid;
-      int hi = kvalid;
-      if (CAUSAL) hi = min(hi, cs.i * Rt + row - cs.j * Rt + 1);
+      const bool row_ok = row_valid(cs, cs.i);
+      int lo = 0, hi;                                      // valid keys [lo, hi) of this tile for this query row
+      if (G > 1) {
+        lo = plo;
+        hi = CAUSAL ? min(plo + L, row + 1) : plo + L;
+      } else {
+        hi = min(Rt, L - cs.j * Rt);
+        if (CAUSAL) hi = min(hi, cs.i * Rt + row - cs.j * Rt + 1);
+      }
       // delta_i = sum_d dO_id * O_id from the swizzled smem tiles (same swizzle in both tiles, so any
       // consistent chunk order gives matching pairs)
       mbar_wait(&qd_full[s], (k >> 1) & 1);
@@ -838,7 +875,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
           float pr[16], ds[16];
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
-            const bool ok = row_ok && (c + jj) < hi;
+            const bool ok = row_ok && (c + jj) < hi && (c + jj) >= lo;
             const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[jj]), scale_log2, -lse2)) : 0.f;
             pr[jj] = pv;
             ds[jj] = pv * (__uint_as_float(dv[jj]) - delta) * p.scale;
@@ -863,7 +900,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
     auto epilogue = [&](int k) {
       const int n = ce.n, h = ce.h, i = ce.i, j = ce.j;
       const bool first_j = j == 0, last_j = j == T - 1;
-      const bool row_ok = row < min(Rt, L - i * Rt);
+      const bool row_ok = row_valid(ce, i);
       float* srow = scr + (long long)(i * Rt + row) * HD;
       float acc[32], acc2[16];
       const bool dq_ok = warp_stores && row_ok;
@@ -918,7 +955,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
           }
         }
         if (i == T - 1) {                          // dK_j, dV_j complete: rows = keys of tile j
-          const bool k_ok = row < min(Rt, L - j * Rt);
+          const bool k_ok = row_valid(ce, j);
           __nv_bfloat16* krow = p.dqkv + ((long long)n * L + j * Rt + row) * pitch + D + h * HD;
           store32(krow + half * 32, kColDk + half * 32, k_ok);
           store32(krow + D + half * 32, kColDv + half * 32, k_ok);
@@ -965,9 +1002,9 @@ static int launch_bwd_flash(const void* qkv, const void* out, const void* dout, 
   p.lse = lse;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   p.L = L; p.H = H; p.batch = batch;
-  flash_tiling(L, p.T, p.Rt, p.npad);
+  flash_tiling(L, kFlMaxRowsBwd, p.T, p.Rt, p.npad, p.G);
   p.scale = 1.0f / sqrtf((float)HD);
-  const long long total = (long long)batch * H;
+  const long long total = (long long)((batch + p.G - 1) / p.G) * H;
   int grid = num_sms();
   if (grid > total) grid = (int)total;
   const long long need = p.T > 1 ? (long long)grid * p.T * p.Rt * HD * 4 : 0;
@@ -997,8 +1034,8 @@ static int launch_bwd_flash(const void* qkv, const void* out, const void* dout, 
 }
 
 long long attention_bwd_flash_workspace(int batch, int L, int H, int hd) {
-  int T, Rt, npad;
-  flash_tiling(L, T, Rt, npad);
+  int T, Rt, npad, G;
+  flash_tiling(L, kFlMaxRowsBwd, T, Rt, npad, G);
   if (T <= 1) return 0;
   long long grid = num_sms();
   if (grid > (long long)batch * H) grid = (long long)batch * H;

@@ -5,10 +5,12 @@ runs on top of this package unchanged.
 Precision flags (training/precision.py:6-15, open_clip/model.py:78-86):
   'bf16'               weights of matmul-like layers are cast to bf16 (convert_weights_to_lp),
                        LayerNorm/embeddings stay fp32 -- the reference's "pure bf16" mode;
-  'amp_bf16'/'amp'/'fp32'  fp32 master weights; the kernels read bf16 shadow copies refreshed after
-                       every optimizer step, gradients are fp32.  (Under the reference's autocast
-                       the matmuls run in bf16 as well; there is no fp32-compute path on the
-                       tensor cores, so plain 'fp32' means "fp32 master weights" here.)
+  'amp_bf16'           fp32 master weights; the kernels read bf16 shadow copies refreshed after every
+                       optimizer step, gradients are fp32 (the reference's autocast runs the same
+                       matmuls in bf16).
+  'fp32' / 'amp' / 'fp16'  NOT computed: no fp32 (or fp16) arithmetic exists on this path.  The model can
+                       be built (state_dict schema, checkpoint conversion) but forward() raises instead of
+                       silently substituting bf16 math.
 """
 from __future__ import annotations
 
@@ -18,7 +20,8 @@ from typing import Any, Dict, Optional, Tuple, Union
 import torch
 
 from .loss import ClipLoss
-from .model import CLIP, convert_weights_to_lp, get_cast_dtype, resize_pos_embed, resize_text_pos_embed
+from .model import (CLIP, COMPUTE_PRECISIONS, CustomTextCLIP, convert_to_custom_text_state_dict, convert_weights_to_lp,
+                    get_cast_dtype, resize_pos_embed, resize_text_pos_embed)
 from .model_configs import add_model_config, get_model_config, list_models  # noqa: F401
 
 OPENAI_DATASET_MEAN = (0.48145466, 0.4578275, 0.40821073)
@@ -38,6 +41,8 @@ def load_checkpoint(model, checkpoint_path, strict=True):
     """open_clip/factory.py:110-118: position tables of the checkpoint are resampled to the model's image
     grid / context length before loading (pre-train at 84-126 px, fine-tune at 224+)."""
     state_dict = load_state_dict(checkpoint_path)
+    if 'positional_embedding' in state_dict and not hasattr(model, 'positional_embedding'):
+        state_dict = convert_to_custom_text_state_dict(state_dict)       # CLIP checkpoint -> CustomTextCLIP keys
     resize_pos_embed(state_dict, model)
     resize_text_pos_embed(state_dict, model)
     return model.load_state_dict(state_dict, strict=strict)
@@ -53,8 +58,8 @@ def create_model(model_name: str, pretrained: Optional[str] = None, precision: s
                  require_pretrained: bool = False, pos_embed: str = None):
     if jit:
         raise NotImplementedError("torch.jit.script is not applicable: blocks are custom CUDA autograd nodes")
-    if force_custom_text or pretrained_image:
-        raise NotImplementedError("CustomTextCLIP / timm image towers are outside the CLIPA hot path")
+    if pretrained_image:
+        raise NotImplementedError("timm image towers are outside the CLIPA hot path")
     model_name = model_name.replace('/', '-')
     if isinstance(device, str):
         device = torch.device(device)
@@ -69,9 +74,15 @@ def create_model(model_name: str, pretrained: Optional[str] = None, precision: s
         model_cfg["vision_cfg"]["image_size"] = force_image_size
     if pos_embed is not None:
         model_cfg["vision_cfg"]["pos_embed"] = pos_embed
-    model_cfg.pop('custom_text', None)
+    custom_text = model_cfg.pop('custom_text', False) or force_custom_text          # factory.py:203-211
     cast_dtype = get_cast_dtype(precision)
-    model = CLIP(**model_cfg, cast_dtype=cast_dtype)
+    model = (CustomTextCLIP if custom_text else CLIP)(**model_cfg, cast_dtype=cast_dtype)
+    # 'fp32' (the reference's default) / 'amp' / 'fp16' models can be built, saved and loaded, but refuse to run:
+    # there is no fp32 or fp16 arithmetic in this library (model.check_compute_precision)
+    model.compute_precision = precision
+    if precision not in COMPUTE_PRECISIONS:
+        logging.warning("precision=%r: built as a parameter container only; forward() needs 'amp_bf16' or 'bf16'",
+                        precision)
     if pretrained:
         import os
         if not os.path.exists(pretrained):

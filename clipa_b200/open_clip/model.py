@@ -14,6 +14,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import functional as Fn
+from .transformer import text_tower_forward  # noqa: E402
 from .transformer import LayerNorm, TextTransformer, VisionTransformer
 
 
@@ -154,30 +155,13 @@ class CLIP(nn.Module):
         self.transformer.grad_checkpointing = enable
 
     def encode_image(self, image, normalize: bool = False):
+        check_compute_precision(self)
         features = self.visual(image)
         return _l2_normalize(features) if normalize else features
 
     def encode_text(self, text, normalize: bool = False):
-        N, L = text.shape
-        if L != self.context_length:
-            raise ValueError(f"text length {L} != context_length {self.context_length} "
-                             "(the reference adds the full positional embedding, model.py:247)")
-        x = self.token_embedding(text).to(torch.bfloat16)
-        x = x + self.positional_embedding.to(torch.bfloat16)
-        W = x.shape[-1]
-        causal = self.attn_mask is not None
-        x = self.transformer(x.reshape(N * L, W).contiguous(), N, L, causal=causal).reshape(N, L, W)
-        # ln_final is row-wise, so normalising only the pooled rows equals model.py:251-254
-        if self.pool_style == 'open_clip':
-            pooled = x[torch.arange(N, device=x.device), text.argmax(dim=-1)]
-        elif self.pool_style == 'big_vision_tok':
-            pooled = x[:, 0]
-        elif self.pool_style == 'big_vision_last':
-            pooled = x[:, -1]
-        else:
-            raise ValueError(self.pool_style)
-        pooled = self.ln_final(pooled.contiguous())
-        x = Fn.LinearFn.apply(pooled, self.text_projection, None, True)
+        check_compute_precision(self)
+        x = text_tower_forward(self, text, slice_positions=False)
         return _l2_normalize(x) if normalize else x
 
     def forward(self, image, text):
@@ -187,6 +171,76 @@ class CLIP(nn.Module):
             return {"image_features": image_features, "text_features": text_features,
                     "logit_scale": self.logit_scale.exp()}
         return image_features, text_features, self.logit_scale.exp()
+
+
+class CustomTextCLIP(nn.Module):
+    """open_clip/model.py:277-326: the text tower stays a sub-module (`text.*` state_dict keys) instead of being
+    re-homed onto the model; selected by `custom_text` in a model config or --force-custom-text."""
+
+    def __init__(self, embed_dim: int, vision_cfg: CLIPVisionCfg, text_cfg: CLIPTextCfg,
+                 quick_gelu: bool = False, cast_dtype: Optional[torch.dtype] = None,
+                 output_dict: bool = False):
+        super().__init__()
+        self.output_dict = output_dict
+        self.visual = _build_vision_tower(embed_dim, vision_cfg, quick_gelu, cast_dtype)
+        self.text = _build_text_tower(embed_dim, text_cfg, quick_gelu, cast_dtype)
+        self.context_length = self.text.context_length
+        self.vocab_size = self.text.vocab_size
+        self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
+
+    def lock_image_tower(self, unlocked_groups=0, freeze_bn_stats=False):
+        self.visual.lock(unlocked_groups=unlocked_groups, freeze_bn_stats=freeze_bn_stats)
+
+    def lock_text_tower(self, unlocked_layers: int = 0, freeze_layer_norm: bool = True):
+        self.text.lock(unlocked_layers, freeze_layer_norm)
+
+    @torch.jit.ignore
+    def set_grad_checkpointing(self, enable=True):
+        self.visual.set_grad_checkpointing(enable)
+        self.text.set_grad_checkpointing(enable)
+
+    def encode_image(self, image, normalize: bool = False):
+        check_compute_precision(self)
+        features = self.visual(image)
+        return _l2_normalize(features) if normalize else features
+
+    def encode_text(self, text, normalize: bool = False):
+        check_compute_precision(self)
+        features = self.text(text)
+        return _l2_normalize(features) if normalize else features
+
+    def forward(self, image, text):
+        image_features = self.encode_image(image, normalize=True)
+        text_features = self.encode_text(text, normalize=True)
+        if self.output_dict:
+            return {"image_features": image_features, "text_features": text_features,
+                    "logit_scale": self.logit_scale.exp()}
+        return image_features, text_features, self.logit_scale.exp()
+
+
+def convert_to_custom_text_state_dict(state_dict: dict):
+    """open_clip/model.py:358-373: CLIP-format checkpoint -> CustomTextCLIP keys (text tower under `text.`)."""
+    if 'text_projection' in state_dict:
+        prefixes = ('text_projection', 'positional_embedding', 'token_embedding', 'transformer', 'ln_final')
+        return {('text.' + k if any(k.startswith(p) for p in prefixes) else k): v for k, v in state_dict.items()}
+    return state_dict
+
+
+# Precision flags whose arithmetic this library implements (training/precision.py, open_clip/model.py:78-86):
+# fp32 master weights with bf16 tensor-core math ('amp_bf16'), or bf16 weights ('bf16').
+COMPUTE_PRECISIONS = ('amp_bf16', 'amp_bfloat16', 'bf16', 'pure_bf16')
+
+
+def check_compute_precision(model) -> None:
+    """A model built with any other flag (the factory's default 'fp32', 'amp' = fp16 autocast, 'fp16') is only a
+    parameter container (state_dict / checkpoint conversion): running it would silently replace the requested
+    arithmetic by bf16 tensor-core math, so it refuses."""
+    flag = getattr(model, 'compute_precision', 'amp_bf16')
+    if flag not in COMPUTE_PRECISIONS:
+        raise NotImplementedError(
+            f"precision={flag!r}: no fp32 / fp16 compute path is built -- the sm_100a kernels multiply in bf16 with "
+            "fp32 accumulation.  Build the model with precision='amp_bf16' (fp32 master weights, the mode of every "
+            "reference GPU script) or 'bf16'.")
 
 
 def resize_pos_embed(state_dict, model, interpolation: str = 'bicubic', antialias: bool = True):

@@ -291,3 +291,58 @@ class TextTransformer(nn.Module):
             nn.init.normal_(block.mlp.c_fc.weight, std=fc_std)
             nn.init.normal_(block.mlp.c_proj.weight, std=proj_std)
         nn.init.normal_(self.text_projection, std=self.transformer.width ** -0.5)
+
+    def lock(self, unlocked_layers: int = 0, freeze_layer_norm: bool = True):
+        """Freeze the text tower, optionally leaving the last `unlocked_layers` blocks (and the final LayerNorm /
+        projection) trainable -- the role of TextTransformer.lock for CustomTextCLIP.lock_text_tower
+        (open_clip/model.py:304-305)."""
+        for p in self.parameters():
+            p.requires_grad = False
+        if unlocked_layers > 0:
+            for blk in self.transformer.resblocks[-unlocked_layers:]:
+                for p in blk.parameters():
+                    p.requires_grad = True
+            self.text_projection.requires_grad = True
+            for p in self.ln_final.parameters():
+                p.requires_grad = not freeze_layer_norm
+
+    @torch.jit.ignore
+    def set_grad_checkpointing(self, enable=True):
+        self.transformer.grad_checkpointing = enable
+
+    def forward(self, text: torch.Tensor):
+        """open_clip/transformer.py:638-681 (no cls_emb): token gather + positional rows [:seq_len] -> blocks ->
+        ln_final -> pool (EOT argmax / first / last) -> text_projection.  Used by CustomTextCLIP."""
+        return text_tower_forward(self, text, slice_positions=True)
+
+
+def text_tower_forward(mod, text: torch.Tensor, slice_positions: bool):
+    """The text tower on the sm_100a kernels, shared by CLIP.encode_text (whose members live on the CLIP
+    module itself, open_clip/model.py:216-225,245-263) and TextTransformer.forward (transformer.py:638-681):
+    `mod` provides token_embedding, positional_embedding, transformer, ln_final, text_projection, attn_mask,
+    pool_style, context_length.  CLIP.encode_text adds the WHOLE positional table (model.py:247: the text
+    length must equal context_length); TextTransformer.forward slices it to the sequence length."""
+    N, L = text.shape
+    if not slice_positions and L != mod.context_length:
+        raise ValueError(f"text length {L} != context_length {mod.context_length} "
+                         "(the reference adds the full positional embedding, model.py:247)")
+    if L > mod.positional_embedding.shape[0]:
+        raise ValueError(f"text length {L} exceeds the {mod.positional_embedding.shape[0]} positions of the tower")
+    x = mod.token_embedding(text).to(torch.bfloat16)
+    x = x + mod.positional_embedding[:L].to(torch.bfloat16)
+    W = x.shape[-1]
+    causal = mod.attn_mask is not None
+    x = mod.transformer(x.reshape(N * L, W).contiguous(), N, L, causal=causal).reshape(N, L, W)
+    # ln_final is row-wise, so normalising only the pooled rows equals model.py:251-254
+    if mod.pool_style == 'open_clip':
+        pooled = x[torch.arange(N, device=x.device), text.argmax(dim=-1)]
+    elif mod.pool_style == 'big_vision_tok':
+        pooled = x[:, 0]
+    elif mod.pool_style == 'big_vision_last':
+        pooled = x[:, -1]
+    else:
+        raise ValueError(mod.pool_style)
+    pooled = mod.ln_final(pooled.contiguous())
+    if mod.text_projection is not None:
+        pooled = Fn.LinearFn.apply(pooled, mod.text_projection, None, True)
+    return pooled

@@ -244,8 +244,11 @@ def clip_softmax_grad(a, b_all, scale, label_offset: int, lse: torch.Tensor,
 
 def adamw_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
                param_bf16: Optional[torch.Tensor], *, lr: float, beta1: float, beta2: float, eps: float,
-               weight_decay: float, step: int, grad_scale: float = 1.0, zero_grad: bool = True) -> None:
-    """Fused AdamW over flat fp32 segments (+ bf16 shadow refresh + gradient clear), in place."""
+               weight_decay: float, step: int, grad_scale: float = 1.0, zero_grad: bool = True,
+               grad_scale_dev: Optional[torch.Tensor] = None) -> None:
+    """Fused AdamW over flat fp32 segments (+ bf16 shadow refresh + gradient clear), in place.
+    grad_scale_dev: optional 1-element fp32 CUDA tensor multiplied into grad_scale on the device
+    (gradient-clipping factor without a host round trip)."""
     n = param.numel()
     for t in (param, grad, exp_avg, exp_avg_sq):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
@@ -254,4 +257,5 @@ def adamw_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, e
     with _prof(("adamw", n), 0.0, (34.0 if param_bf16 is not None else 32.0) * n):
         check(_lib.lib().clipa_adamw_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq),
                                           _ptr(param_bf16), n, lr, beta1, beta2, eps, weight_decay, step,
-                                          grad_scale, int(zero_grad), _stream()), "clipa_adamw_step")
+                                          grad_scale, _ptr(grad_scale_dev), int(zero_grad), _stream()),
+              "clipa_adamw_step")

@@ -38,11 +38,16 @@ class TrainStep:
                  lr: float = 1.024e-3, betas: Tuple[float, float] = (0.9, 0.95), eps: float = 1e-6,
                  wd: float = 0.2, micro_batch: int = 4096, local_loss: bool = True,
                  gather_with_grad: bool = True, image_mean=None, image_std=None,
-                 grad_clip_norm: Optional[float] = None, fused_optimizer: bool = True):
+                 grad_clip_norm: Optional[float] = None, fused_optimizer: bool = True,
+                 reference_accum_logit_scale: bool = True):
         self.model = model
         self.rank, self.world_size = rank, world_size
         self.micro_batch = micro_batch
         self.grad_clip_norm = grad_clip_norm
+        # train.py:243-256 calls backward() once per accumulation chunk on the FULL loss, so the reference's
+        # logit_scale gradient is accumulated accum_freq times (tower parameters are not: chunk j only reaches
+        # them through its own features).  Reproduced by default; False gives the single-pass gradient.
+        self.reference_accum_logit_scale = reference_accum_logit_scale
         self.loss_fn = open_clip.ClipLoss(local_loss=local_loss, gather_with_grad=gather_with_grad,
                                           cache_labels=True, rank=rank, world_size=world_size)
         dev = next(model.parameters()).device
@@ -61,14 +66,15 @@ class TrainStep:
         self._flat = {}
         if self.fused:
             # fp32 master weights: parameters, gradients, Adam moments and the bf16 shadow weights of
-            # each weight-decay group live in flat buffers (every tensor padded to 4 elements = 16 B),
+            # each weight-decay group live in flat buffers (every tensor padded to 8 elements: the fp32
+            # segments and the bf16 shadows -- TMA operands -- all start 16-byte aligned),
             # so one optimizer step is two launches of clipa_adamw_step and the data-parallel
             # gradient reduction is one all-reduce per group.
             self._groups = []
             for ps, group_wd in ((gain, 0.0), (rest, wd)):
                 if not ps:
                     continue
-                sizes = [(p.numel() + 3) // 4 * 4 for p in ps]
+                sizes = [(p.numel() + 7) // 8 * 8 for p in ps]
                 total = sum(sizes)
                 fp = torch.zeros(total, dtype=torch.float32, device=dev)
                 fg = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -84,7 +90,8 @@ class TrainStep:
                     shadow.copy_(p.data)
                     p._clipa_bf16 = (p._version, shadow)
                     off += sz
-                self._groups.append(dict(p=fp, g=fg, m=torch.zeros_like(fp), v=torch.zeros_like(fp), b=fb, wd=group_wd))
+                self._groups.append(dict(p=fp, g=fg, m=torch.zeros_like(fp), v=torch.zeros_like(fp), b=fb, wd=group_wd,
+                                         params=ps, sizes=sizes))
                 self._flat[len(self._groups)] = fg
             self.optimizer = None
         else:
@@ -120,7 +127,7 @@ class TrainStep:
                 if average:
                     flat.div_(self.world_size)
 
-    def optimizer_step(self, grad_scale: float = 1.0):
+    def optimizer_step(self, grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None):
         """AdamW update; with the fused kernel the 1/world_size averaging, the bf16 shadow refresh and the
         clearing of the gradient buffers ride along in the same pass."""
         if not self.fused:
@@ -139,7 +146,49 @@ class TrainStep:
         for grp in self._groups:
             ops.adamw_step(grp["p"], grp["g"], grp["m"], grp["v"], grp["b"], lr=self.lr, beta1=self.betas[0],
                            beta2=self.betas[1], eps=self.eps, weight_decay=grp["wd"], step=self.step_count,
-                           grad_scale=grad_scale, zero_grad=True)
+                           grad_scale=grad_scale, grad_scale_dev=grad_scale_dev, zero_grad=True)
+
+    # ---- checkpoint / resume (training/main.py:352-369 saves optimizer.state_dict(); --resume restores it) ----
+    def state_dict(self) -> dict:
+        """torch.optim.AdamW-compatible optimizer state (same param order as main.py:318-326: the no-decay group
+        first, then the decayed one), so checkpoints move between the reference's optimizer and this step."""
+        if not self.fused:
+            return self.optimizer.state_dict()
+        state, groups, idx = {}, [], 0
+        for grp in self._groups:
+            ids, off = [], 0
+            for p, sz in zip(grp["params"], grp["sizes"]):
+                n = p.numel()
+                state[idx] = {"step": torch.tensor(float(self.step_count)),
+                              "exp_avg": grp["m"][off:off + n].view_as(p).clone(),
+                              "exp_avg_sq": grp["v"][off:off + n].view_as(p).clone()}
+                ids.append(idx)
+                idx += 1
+                off += sz
+            groups.append({"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": grp["wd"],
+                           "amsgrad": False, "maximize": False, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if not self.fused:
+            self.optimizer.load_state_dict(sd)
+            return
+        steps = set()
+        for grp, g_sd in zip(self._groups, sd["param_groups"]):
+            assert len(g_sd["params"]) == len(grp["params"]), "optimizer state does not match the parameter groups"
+            off = 0
+            for p, sz, pid in zip(grp["params"], grp["sizes"], g_sd["params"]):
+                st = sd["state"].get(pid)
+                n = p.numel()
+                if st is not None:
+                    grp["m"][off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    grp["v"][off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(int(float(st["step"])))
+                off += sz
+        if sd["param_groups"]:
+            self.lr = sd["param_groups"][0].get("lr", self.lr)
+        assert len(steps) <= 1, f"per-parameter step counts differ: {sorted(steps)}"
+        self.step_count = steps.pop() if steps else 0
 
     def forward_backward(self, images: torch.Tensor, texts: torch.Tensor) -> torch.Tensor:
         model = self.model
@@ -157,9 +206,18 @@ class TrainStep:
         # its graph -- only one chunk's activations are alive at a time either way -- so its second
         # forward is saved: N chunks cost 2N-1 forwards instead of 2N (same numbers, same peak memory).
         (ls, le) = chunks[-1]
+        # Stochastic layers (PatchDropout draws fresh scores per call, transformer.py:76-82) must keep the SAME
+        # tokens in a chunk's second forward, or the cached d(features) would be applied to features they were
+        # not computed for: snapshot the device RNG before each no-grad forward and restore it for the re-run
+        # (GradCache's RandContext).  The reference recomputes the loss from the re-run features instead.
+        stochastic = model.training and any(getattr(m, "prob", 0.) > 0. for m in model.modules()
+                                            if type(m).__name__ == "PatchDropout")
+        rng = []
         with torch.no_grad():
             fi, ft = [], []
             for s, e in chunks[:-1]:
+                if stochastic:
+                    rng.append(torch.cuda.get_rng_state(self.device))
                 a, b, _ = self._unpack(model(images[s:e], texts[s:e]))
                 fi.append(a)
                 ft.append(b)
@@ -168,11 +226,19 @@ class TrainStep:
         ft = torch.cat(ft + [b_last.detach()]).requires_grad_(True)
         loss = self.loss_fn(fi, ft, model.logit_scale.exp())
         loss.backward()
+        if self.reference_accum_logit_scale and model.logit_scale.grad is not None:
+            model.logit_scale.grad.mul_(len(chunks))
         torch.autograd.backward([a_last, b_last], [fi.grad[ls:le], ft.grad[ls:le]])
         del a_last, b_last
-        for s, e in chunks[:-1]:
+        if stochastic:
+            after = torch.cuda.get_rng_state(self.device)
+        for c, (s, e) in enumerate(chunks[:-1]):
+            if stochastic:
+                torch.cuda.set_rng_state(rng[c], self.device)
             a, b, _ = self._unpack(model(images[s:e], texts[s:e]))
             torch.autograd.backward([a, b], [fi.grad[s:e], ft.grad[s:e]])
+        if stochastic:
+            torch.cuda.set_rng_state(after, self.device)
         return loss.detach()
 
     @staticmethod
@@ -191,13 +257,16 @@ class TrainStep:
         loss = self.forward_backward(images, texts)
         self._allreduce_grads(average=not self.fused)
         scale = 1.0 / self.world_size if self.fused else 1.0
+        clip = None
         if self.grad_clip_norm is not None:
-            if self.fused:   # ||scale * g|| over all groups; folded into the kernel's grad_scale
-                total = torch.sqrt(sum((f.float() ** 2).sum() for f in self._flat.values())).item() * scale
-                scale *= min(1.0, self.grad_clip_norm / (total + 1e-6))
+            if self.fused:
+                # clip_grad_norm_ (train.py:277-283): factor min(1, max_norm / (||g|| + 1e-6)) with g the averaged
+                # gradient; computed on the device and handed to the optimizer kernel as a pointer (no .item())
+                total = torch.sqrt(sum(torch.linalg.vector_norm(f) ** 2 for f in self._flat.values())) * scale
+                clip = torch.clamp(self.grad_clip_norm / (total + 1e-6), max=1.0).reshape(1).float()
             else:
                 torch.nn.utils.clip_grad_norm_(self.params, self.grad_clip_norm, norm_type=2.0)
-        self.optimizer_step(grad_scale=scale)
+        self.optimizer_step(grad_scale=scale, grad_scale_dev=clip)
         with torch.no_grad():
             self.model.logit_scale.clamp_(0, math.log(100))
         return loss

@@ -160,10 +160,12 @@ int clipa_clip_softmax_grad(const void* a, const void* b_all, int32_t b_local, i
  *   p -= (lr / (1-b1^step)) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
  * In the same pass it refreshes the bf16 shadow copy the GEMMs read (param_bf16, may be NULL) and,
  * if zero_grad != 0, clears the gradient segment for the next step.  n must be a multiple of 4 and
- * every buffer 16-byte aligned; `step` counts from 1. */
+ * every buffer 16-byte aligned; `step` counts from 1.  grad_scale_dev (may be NULL): f32 scalar in device
+ * memory multiplied into grad_scale inside the kernel -- the clip_grad_norm_ factor of train.py:277-283
+ * without reading the gradient norm back to the host. */
 int clipa_adamw_step(void* param, void* grad, void* exp_avg, void* exp_avg_sq, void* param_bf16, int64_t n,
                      float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                     float grad_scale, int32_t zero_grad, void* stream);
+                     float grad_scale, const float* grad_scale_dev, int32_t zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -134,7 +134,8 @@ def test_gradcache_schedule_matches_single_pass_cpu():
     grads = []
     for mb in (10, 4, 3):
         model = Toy()
-        ts = TrainStep(model, micro_batch=mb, image_mean=(0., 0., 0.), image_std=(1., 1., 1.))
+        ts = TrainStep(model, micro_batch=mb, image_mean=(0., 0., 0.), image_std=(1., 1., 1.),
+                       reference_accum_logit_scale=False)
         ts.loss_fn = loss_fn
         loss = ts.forward_backward(images, texts)
         n_chunks = -(-10 // mb)
@@ -144,6 +145,52 @@ def test_gradcache_schedule_matches_single_pass_cpu():
         assert abs(l - grads[0][0]) < 1e-6
         for a, b in zip(g, grads[0][1]):
             assert torch.allclose(a, b, atol=1e-6, rtol=1e-5)
+    # default: the reference's accumulation loop (train.py:243-256) back-propagates the FULL loss once per chunk,
+    # so its logit_scale gradient is n_chunks x the single-pass one; every other parameter is unaffected
+    model = Toy()
+    ts = TrainStep(model, micro_batch=4, image_mean=(0., 0., 0.), image_std=(1., 1., 1.))
+    ts.loss_fn = loss_fn
+    ts.forward_backward(images, texts)
+    single = dict(zip([id(p) for p in grads[0][1]], grads[0][1]))
+    for (name, p), ref in zip(model.named_parameters(), grads[0][1]):
+        if name == "logit_scale":
+            assert torch.allclose(p.grad, 3 * ref, atol=1e-6, rtol=1e-5)
+        else:
+            assert torch.allclose(p.grad, ref, atol=1e-6, rtol=1e-5)
+
+
+def test_reference_accumulation_multiplies_the_logit_scale_gradient():
+    """The quirk reproduced above, checked against the reference's own loop body (train.py:216-256) run on the
+    same toy model: cached no-grad features, then per chunk a re-forward + full loss + backward."""
+    import torch
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    vis, txt = torch.nn.Linear(12, 8), torch.nn.Linear(5, 8)
+    logit_scale = torch.nn.Parameter(torch.tensor(2.0))
+    x, y = torch.randn(9, 12), torch.randn(9, 5)
+
+    def fwd(a, b):
+        return F.normalize(vis(a), dim=-1), F.normalize(txt(b), dim=-1), logit_scale.exp()
+
+    def loss_fn(i, t, s):
+        lg = s * i @ t.t()
+        lab = torch.arange(i.shape[0])
+        return (F.cross_entropy(lg, lab) + F.cross_entropy(lg.t(), lab)) / 2
+    loss_fn(*fwd(x, y)).backward()
+    g_single = logit_scale.grad.clone()
+    g_w = vis.weight.grad.clone()
+    for p in (vis.weight, vis.bias, txt.weight, txt.bias, logit_scale):
+        p.grad = None
+    chunks = [(0, 3), (3, 6), (6, 9)]
+    with torch.no_grad():
+        cache = [fwd(x[s:e], y[s:e])[:2] for s, e in chunks]
+    for j, (s, e) in enumerate(chunks):                 # train.py:243-256
+        i_j, t_j, sc = fwd(x[s:e], y[s:e])
+        ii = torch.cat([c[0] for c in cache[:j]] + [i_j] + [c[0] for c in cache[j + 1:]])
+        tt = torch.cat([c[1] for c in cache[:j]] + [t_j] + [c[1] for c in cache[j + 1:]])
+        loss_fn(ii, tt, sc).backward()
+    assert torch.allclose(logit_scale.grad, 3 * g_single, rtol=1e-5)
+    assert torch.allclose(vis.weight.grad, g_w, rtol=1e-4, atol=1e-6)
 
 
 def _host_gold():
@@ -247,3 +294,86 @@ def test_grad_sink_is_opt_in():
     q.grad = torch.zeros(8, 4)
     q.grad = q.grad.t().contiguous().t()                                 # non-contiguous view
     assert grad_sink(q) is None
+
+
+def test_unbuilt_precisions_refuse_to_run():
+    """precision='fp32' (the factory default), 'amp' and 'fp16' have no arithmetic on this path: the model is a
+    parameter container (schema / checkpoints) and forward() raises instead of silently running bf16 math."""
+    import torch
+    from clipa_b200 import open_clip
+    m = open_clip.create_model("ViT-B-32-CL16", precision="fp32", device="cpu", force_image_size=64)
+    assert m.compute_precision == "fp32" and next(m.parameters()).dtype == torch.float32
+    with pytest.raises(NotImplementedError, match="amp_bf16"):
+        m(torch.zeros(1, 3, 64, 64), torch.zeros(1, 16, dtype=torch.long))
+    with pytest.raises(NotImplementedError, match="amp_bf16"):
+        m.encode_text(torch.zeros(1, 16, dtype=torch.long))
+    with pytest.raises(NotImplementedError):
+        open_clip.create_model("ViT-B-32-CL16", precision="fp16", device="cpu")
+    ok = open_clip.create_model("ViT-B-32-CL16", precision="amp_bf16", device="cpu", force_image_size=64)
+    with pytest.raises(Exception) as e:     # the precision check passes; the kernels then refuse CPU tensors
+        ok.encode_text(torch.zeros(1, 16, dtype=torch.long))
+    assert not isinstance(e.value, NotImplementedError)
+
+
+def test_custom_text_clip_schema_and_checkpoint_conversion():
+    """CustomTextCLIP (open_clip/model.py:277-326, --force-custom-text): text tower under `text.*`, same tensors
+    as CLIP; a CLIP-format checkpoint loads through convert_to_custom_text_state_dict (factory.py:110-118)."""
+    import torch
+    from clipa_b200 import open_clip
+    clip = open_clip.create_model("ViT-B-32-CL16", precision="amp_bf16", device="cpu", force_image_size=64)
+    ct = open_clip.create_model("ViT-B-32-CL16", precision="amp_bf16", device="cpu", force_image_size=64,
+                                force_custom_text=True)
+    assert isinstance(ct, open_clip.CustomTextCLIP) and isinstance(ct.text, open_clip.TextTransformer)
+    sd = clip.state_dict()
+    conv = open_clip.convert_to_custom_text_state_dict(sd)
+    assert set(conv) == set(ct.state_dict())
+    assert {k for k in conv if k.startswith("text.")} == {"text." + k for k in sd if k.split(".")[0] in
+                                                          ("text_projection", "positional_embedding", "token_embedding",
+                                                           "transformer", "ln_final")}
+    ct.load_state_dict(conv, strict=True)
+    assert torch.equal(ct.text.text_projection, clip.text_projection)
+    assert ct.context_length == 16 and ct.vocab_size == clip.vocab_size
+    ct.lock_text_tower(unlocked_layers=1)
+    assert not ct.text.token_embedding.weight.requires_grad
+    assert ct.text.transformer.resblocks[-1].mlp.c_fc.weight.requires_grad
+    assert not ct.text.transformer.resblocks[0].mlp.c_fc.weight.requires_grad
+
+
+def test_train_step_optimizer_state_dict_is_adamw_compatible():
+    """TrainStep.state_dict()/load_state_dict(): torch.optim.AdamW layout (state[idx] = step / exp_avg /
+    exp_avg_sq, two param groups in main.py:318-326 order), so --resume checkpoints interchange with the
+    reference optimizer; flat segments are padded to 8 elements (16-byte aligned bf16 shadows)."""
+    import torch
+    from clipa_b200.training import TrainStep, exclude_from_wd
+    torch.manual_seed(0)
+    model = torch.nn.Sequential()
+    model.visual = torch.nn.Linear(5, 3)            # 15 + 3 elements: not multiples of 8
+    model.ln = torch.nn.LayerNorm(3)
+    model.logit_scale = torch.nn.Parameter(torch.tensor(1.0))
+    ts = TrainStep(model, micro_batch=4, image_mean=(0., 0., 0.), image_std=(1., 1., 1.))
+    assert ts.fused
+    for grp in ts._groups:
+        assert all(sz % 8 == 0 for sz in grp["sizes"])
+        off = 0
+        for p, sz in zip(grp["params"], grp["sizes"]):
+            assert p.data_ptr() == grp["p"][off:].data_ptr() and (p.data_ptr() - grp["p"].data_ptr()) % 32 == 0
+            off += sz
+    named = list(model.named_parameters())
+    gain = [p for n, p in named if exclude_from_wd(n, p)]
+    rest = [p for n, p in named if not exclude_from_wd(n, p)]
+    ref = torch.optim.AdamW([{"params": gain, "weight_decay": 0.}, {"params": rest, "weight_decay": 0.2}],
+                            lr=1e-3, betas=(0.9, 0.95), eps=1e-6)
+    for p in gain + rest:
+        p.grad = torch.randn_like(p)
+    ref.step()
+    ref_sd = ref.state_dict()
+    ts.load_state_dict(ref_sd)
+    assert ts.step_count == 1
+    mine = ts.state_dict()
+    assert [g["params"] for g in mine["param_groups"]] == [g["params"] for g in ref_sd["param_groups"]]
+    assert [g["weight_decay"] for g in mine["param_groups"]] == [0.0, 0.2]
+    for k, st in ref_sd["state"].items():
+        assert torch.equal(mine["state"][k]["exp_avg"], st["exp_avg"])
+        assert torch.equal(mine["state"][k]["exp_avg_sq"], st["exp_avg_sq"])
+        assert float(mine["state"][k]["step"]) == float(st["step"])
+    ref.load_state_dict(mine)                       # and back into the reference optimizer

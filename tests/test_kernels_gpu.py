@@ -204,7 +204,10 @@ def _attention_case(dev, B, L, H, hd, causal, tol_out=2e-2, tol_grad=3e-2):
     (1, 577, 2, 80, False), (2, 401, 2, 64, False), (3, 129, 4, 64, False), (2, 192, 2, 64, True),
     (2, 193, 2, 80, True), (2, 97, 4, 80, False), (3, 96, 4, 80, True), (5, 82, 16, 64, False),
     (2, 16, 12, 64, True), (3, 8, 16, 80, True), (1, 1, 2, 80, False), (40, 257, 16, 64, False),
-    (700, 37, 16, 80, False), (30, 65, 16, 80, False), (9, 128, 8, 64, True)])
+    (700, 37, 16, 80, False), (30, 65, 16, 80, False), (9, 128, 8, 64, True),
+    # packed short sequences (block-diagonal tiles): partial last tile, causal, G*L < tile rows
+    (5, 37, 16, 80, False), (7, 33, 4, 64, True), (300, 16, 12, 64, True), (11, 48, 2, 80, True), (4, 64, 2, 64, False),
+    (1, 5, 2, 64, True), (1, 577, 2, 80, True)])
 def test_attention_flash(dev, flash_mode, B, L, H, hd, causal):
     _attention_case(dev, B, L, H, hd, causal)
 

@@ -120,7 +120,8 @@ def main():
     if "check" in what:
         cases = [(2, 37, 16, 80, False), (2, 82, 4, 64, False), (2, 257, 4, 64, False), (2, 257, 4, 80, False),
                  (3, 129, 4, 64, False), (2, 192, 2, 64, True), (2, 193, 2, 80, True), (1, 577, 2, 64, False),
-                 (40, 257, 16, 64, False), (700, 37, 16, 80, False), (2, 16, 12, 64, True), (1, 1, 2, 80, False)]
+                 (40, 257, 16, 64, False), (700, 37, 16, 80, False), (2, 16, 12, 64, True), (1, 1, 2, 80, False),
+                 (5, 37, 16, 80, False), (7, 33, 4, 64, True), (300, 16, 12, 64, True), (11, 48, 2, 80, True)]
         n_ok = sum(check_case(*c, dev) for c in cases)
         print(f"GROUP flash check: {n_ok}/{len(cases)} ok")
     if "perf" in what:
