@@ -318,3 +318,82 @@ def test_activation_policy_save_ln_equals_recompute(dev):
     assert l0 == l1
     for n in g0:
         assert rel_err(g0[n].cpu(), g1[n].cpu()) < 1e-3, n     # only fp32-atomic summation order differs
+
+
+def test_custom_text_clip_matches_clip(dev):
+    """CustomTextCLIP (open_clip/model.py:277-326; text tower under `text.`, TextTransformer.forward
+    transformer.py:638-681) computes the same features, loss and gradients as CLIP on converted weights."""
+    import tempfile
+    from clipa_b200 import open_clip
+    from oracle.weights import make_inputs, make_state_dict
+    meta, _ = load_golden("tiny-cls", "fp32")
+    clip = build_model(meta, "amp_bf16", dev)
+    ct, _, _ = open_clip.create_model_and_transforms(f"golden-{meta['name']}", precision="amp_bf16", device=dev,
+                                                     force_image_size=meta["image_size"], pos_embed=meta["pos_embed"],
+                                                     output_dict=True, force_custom_text=True)
+    assert isinstance(ct, open_clip.CustomTextCLIP)
+    ct.load_state_dict(open_clip.convert_to_custom_text_state_dict(clip.state_dict()), strict=True)
+    ct.train()
+    images, text = make_inputs(meta["cfg"], meta["batch"], meta["seed"] + 1000, image_size=meta["image_size"])
+    images, text = images.to(dev), text.to(dev)
+    outs = []
+    for m in (clip, ct):
+        o = m(images, text)
+        loss = open_clip.ClipLoss()(o["image_features"], o["text_features"], o["logit_scale"])
+        loss.backward()
+        outs.append((o, loss))
+    assert torch.equal(outs[0][0]["text_features"], outs[1][0]["text_features"])
+    assert torch.equal(outs[0][0]["image_features"], outs[1][0]["image_features"])
+    assert outs[0][1].item() == outs[1][1].item()
+    g0 = clip.transformer.resblocks[0].attn.in_proj_weight.grad
+    g1 = ct.text.transformer.resblocks[0].attn.in_proj_weight.grad
+    assert torch.allclose(g0, g1, rtol=1e-4, atol=1e-7)       # fp32 atomics: same sum, different order
+    # TextTransformer.forward slices the position table: a shorter text runs (CLIP.encode_text refuses it)
+    short = text[:, :8].clone()
+    short[:, -1] = meta["cfg"]["text_cfg"]["vocab_size"] - 1
+    with torch.no_grad():
+        assert ct.encode_text(short).shape == (meta["batch"], meta["cfg"]["embed_dim"])
+        with pytest.raises(ValueError):
+            clip.encode_text(short)
+
+
+def test_fp32_precision_refuses_to_run_on_gpu(dev):
+    from clipa_b200 import open_clip
+    m = open_clip.create_model("ViT-B-32-CL16", precision="fp32", device=dev, force_image_size=64)
+    with pytest.raises(NotImplementedError, match="amp_bf16"):
+        m(torch.zeros(2, 3, 64, 64, device=dev), torch.zeros(2, 16, dtype=torch.long, device=dev))
+
+
+def test_device_side_grad_clip_and_resume(dev):
+    """TrainStep with grad_clip_norm: the clip factor is computed and applied on the device (no .item()); the step
+    equals torch's clip_grad_norm_ + AdamW.  state_dict()/load_state_dict() resume: a restored trainer continues
+    on the same trajectory as the uninterrupted one."""
+    from clipa_b200.training import TrainStep
+    from oracle.weights import make_inputs
+    meta, _ = load_golden("tiny-cls", "fp32")
+    images, text = make_inputs(meta["cfg"], 6, 5, image_size=meta["image_size"])
+    images, text = images.to(dev), text.to(dev)
+
+    def run(fused, steps, resume_at=None):
+        model = build_model(meta, "amp_bf16", dev)
+        ts = TrainStep(model, micro_batch=16, lr=1e-3, grad_clip_norm=0.5, fused_optimizer=fused)
+        losses = []
+        for i in range(steps):
+            if resume_at is not None and i == resume_at:
+                sd_opt, sd_model = ts.state_dict(), {k: v.clone() for k, v in model.state_dict().items()}
+                model = build_model(meta, "amp_bf16", dev)
+                model.load_state_dict(sd_model)
+                ts = TrainStep(model, micro_batch=16, lr=1e-3, grad_clip_norm=0.5, fused_optimizer=fused)
+                ts.load_state_dict(sd_opt)
+            losses.append(ts.step(images, text).item())
+        return losses, model
+    l_fused, m_fused = run(True, 4)
+    l_torch, m_torch = run(False, 4)
+    for a, b in zip(l_fused, l_torch):
+        assert abs(a - b) < 5e-3 * abs(b), (l_fused, l_torch)
+    w_f = m_fused.visual.transformer.resblocks[0].mlp.c_fc.weight.float()
+    w_t = m_torch.visual.transformer.resblocks[0].mlp.c_fc.weight.float()
+    assert ((w_f - w_t).norm() / w_t.norm()).item() < 2e-3
+    l_res, _ = run(True, 4, resume_at=2)
+    for a, b in zip(l_res, l_fused):
+        assert abs(a - b) < 2e-3 * abs(b), (l_res, l_fused)
