@@ -73,7 +73,28 @@ _SIGNATURES = {
     "clipa_clip_softmax_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "clipa_preprocess_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]),
+    "clipa_patchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_void_p]),
+    "clipa_assemble_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                        C.c_int32, C.c_void_p]),
+    "clipa_assemble_tokens_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "clipa_embed_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_void_p]),
+    "clipa_embed_tokens_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_void_p]),
+    "clipa_pool_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p]),
+    "clipa_pool_tokens_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_void_p]),
+    "clipa_l2_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                     C.c_void_p]),
+    "clipa_l2_normalize_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_int32, C.c_void_p]),
 }
+
+POOL_FIRST, POOL_LAST, POOL_ARGMAX_ID, POOL_MEAN_ALL, POOL_MEAN_SKIP_FIRST = 0, 1, 2, 3, 4
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

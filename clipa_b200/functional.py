@@ -290,3 +290,107 @@ class ClipLossFn(torch.autograd.Function):
                 None if d_all_img is None else (d_all_img * g).to(fdt),
                 None if d_all_txt is None else (d_all_txt * g).to(fdt),
                 (ds * g).reshape(()).to(sdt), None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# tower heads and tails (csrc/tower_io.cu): one kernel per pass instead of torch indexing / elementwise chains
+# ------------------------------------------------------------------------------------------------
+def _sink_or_zeros(p: torch.Tensor, shape=None):
+    sink = grad_sink(p)
+    if sink is not None:
+        return sink, True
+    return torch.zeros(shape or p.shape, dtype=torch.float32, device=p.device), False
+
+
+class AssembleTokensFn(torch.autograd.Function):
+    """[cls; patch tokens] + positional table (open_clip/transformer.py:495-499).  tok: [n*(L-1), W] bf16."""
+
+    @staticmethod
+    def forward(ctx, tok, cls, pos, n, L):
+        x = ops.assemble_tokens(tok.contiguous(), _f32(cls).contiguous(), _f32(pos).contiguous(), n, L)
+        ctx.save_for_backward(cls, pos)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        cls, pos = ctx.saved_tensors
+        dx = dx.contiguous()
+        n, L, W = dx.shape
+        dtok = ops.assemble_tokens_bwd(dx) if ctx.needs_input_grad[0] else None
+        flat = dx.view(n, L * W)
+        dcls = dpos = None
+        if ctx.needs_input_grad[2]:          # learnable table: column sums over the samples; row 0 is also d(cls)
+            buf, direct = _sink_or_zeros(pos)
+            before = buf.view(-1)[:W].clone() if (direct and ctx.needs_input_grad[1]) else None
+            ops.colsum_accum(flat, buf.view(-1))
+            dpos = None if direct else buf.to(pos.dtype)
+            if ctx.needs_input_grad[1]:
+                row0 = buf.view(-1)[:W] - before if before is not None else buf.view(-1)[:W]
+                cbuf, cdirect = _sink_or_zeros(cls)
+                cbuf.add_(row0)
+                dcls = None if cdirect else cbuf.to(cls.dtype)
+        elif ctx.needs_input_grad[1]:        # fixed sin-cos table: only d(cls) = sum_n dx[n, 0, :]
+            cbuf, cdirect = _sink_or_zeros(cls)
+            ops.colsum_accum(flat[:, :W], cbuf)
+            dcls = None if cdirect else cbuf.to(cls.dtype)
+        return dtok, dcls, dpos, None, None
+
+
+class EmbedTokensFn(torch.autograd.Function):
+    """token_embedding(text) + positional rows (open_clip/model.py:245-247)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, pos):
+        ids = ids.contiguous()
+        x = ops.embed_tokens(ids, _f32(table).contiguous(), _f32(pos).contiguous())
+        ctx.save_for_backward(ids, table, pos)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        ids, table, pos = ctx.saved_tensors
+        dx = dx.contiguous()
+        n, L, W = dx.shape
+        dtable = dpos = None
+        if ctx.needs_input_grad[1]:
+            buf, direct = _sink_or_zeros(table)
+            ops.embed_tokens_bwd(ids, dx, buf)
+            dtable = None if direct else buf.to(table.dtype)
+        if ctx.needs_input_grad[2]:
+            buf, direct = _sink_or_zeros(pos)
+            ops.colsum_accum(dx.view(n, L * W), buf.view(-1)[:L * W])
+            dpos = None if direct else buf.to(pos.dtype)
+        return None, dtable, dpos
+
+
+class PoolTokensFn(torch.autograd.Function):
+    """CLS / first / last / EOT-argmax row or token mean of [n, L, W] (transformer.py:509-529, model.py:251-262)."""
+
+    @staticmethod
+    def forward(ctx, x, mode, ids):
+        x = x.contiguous()
+        ids = ids.contiguous() if ids is not None else None
+        ctx.mode, ctx.L = mode, x.shape[1]
+        ctx.save_for_backward(ids)
+        return ops.pool_tokens(x, mode, ids)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        return ops.pool_tokens_bwd(dout.contiguous(), ctx.mode, ctx.L, ids), None, None
+
+
+class L2NormalizeFn(torch.autograd.Function):
+    """F.normalize(dim=-1) (open_clip/model.py:240,263); `out` may be the rank's slice of an all-gather buffer."""
+
+    @staticmethod
+    def forward(ctx, x, out):
+        x = x.contiguous()
+        y, inv = ops.l2_normalize(x, out)
+        ctx.save_for_backward(x, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, inv = ctx.saved_tensors
+        return ops.l2_normalize_bwd(x, inv, dy.contiguous()), None

@@ -122,6 +122,8 @@ def _build_text_tower(embed_dim, text_cfg, quick_gelu=False, cast_dtype=None):
 def _l2_normalize(x: torch.Tensor) -> torch.Tensor:
     """F.normalize(dim=-1) (open_clip/model.py:240,263); the norm is taken in fp32, the result is
     rounded once to the feature dtype (bf16) that the contrastive-head GEMM consumes."""
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.shape[1] % 8 == 0:
+        return Fn.L2NormalizeFn.apply(x, None)
     return F.normalize(x.float(), dim=-1).to(x.dtype)
 
 

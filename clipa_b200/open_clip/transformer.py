@@ -16,6 +16,8 @@ import torch
 from torch import nn
 
 from .. import functional as Fn
+from .. import ops
+from .._lib import POOL_ARGMAX_ID, POOL_FIRST, POOL_LAST, POOL_MEAN_ALL, POOL_MEAN_SKIP_FIRST
 from ..ops import ACT_BY_NAME
 from .pos_embed import get_2d_sincos_pos_embed
 
@@ -213,21 +215,43 @@ class VisionTransformer(nn.Module):
         W = self.width
         # conv1 (stride == kernel, no bias) == patchify + GEMM (open_clip/transformer.py:371,491-493).
         # K = 3*ph*pw is zero-padded to a multiple of 8 so TMA row pitches stay 16-byte aligned.
-        x = x.to(torch.bfloat16)
         K = 3 * ph * pw
         Kp = (K + 7) // 8 * 8
-        patches = x.reshape(N, 3, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(N * gh * gw, K)
+        if x.dtype not in (torch.bfloat16, torch.float32):
+            x = x.float()
+        patches = ops.patchify(x.contiguous(), ph, pw, Kp)          # [N*gh*gw, Kp] bf16, one pass
         wmat = self.conv1.weight.reshape(W, K)
         if Kp != K:
-            patches = torch.nn.functional.pad(patches, (0, Kp - K))
             wmat = torch.nn.functional.pad(wmat, (0, Kp - K))
-        tok = Fn.LinearFn.apply(patches.contiguous(), wmat, None, False).reshape(N, gh * gw, W)
-        cls = self.class_embedding.to(tok.dtype).reshape(1, 1, W).expand(N, 1, W)
-        x = torch.cat([cls, tok], dim=1) + self.positional_embedding.to(tok.dtype)
-        x = self.patch_dropout(x)          # after the positional embedding, before ln_pre (transformer.py:501-502)
-        L = x.shape[1]
+        tok = Fn.LinearFn.apply(patches, wmat, None, False)
+        L = gh * gw + 1
+        dropping = isinstance(self.patch_dropout, PatchDropout) and self.training and self.patch_dropout.prob > 0.
+        x = Fn.AssembleTokensFn.apply(tok, self.class_embedding, self.positional_embedding, N, L)   # [N, L, W]
+        if dropping:
+            x = self.patch_dropout(x)      # after the positional embedding, before ln_pre (transformer.py:501-502)
+            L = x.shape[1]
         x = self.ln_pre(x)
         x = self.transformer(x.reshape(N * L, W).contiguous(), N, L, causal=False).reshape(N, L, W)
+        if self.output_tokens:
+            return self._forward_tail_with_tokens(x)
+        # pooling is a row selection / token mean, LayerNorm is row-wise: ln_post runs on the pooled rows only
+        # (big_vision_tok applies it to every token first, transformer.py:518-520 -- same pooled rows)
+        if self.pool_style in ("open_clip", "big_vision_tok"):
+            if self.pool_style == "big_vision_tok":
+                assert not self.global_average_pool
+            mode = POOL_MEAN_ALL if self.global_average_pool else POOL_FIRST
+        elif self.pool_style == "big_vision_gap":
+            assert self.global_average_pool
+            mode = POOL_MEAN_SKIP_FIRST
+        else:
+            raise ValueError(self.pool_style)
+        pooled = self.ln_post(Fn.PoolTokensFn.apply(x, mode, None))
+        if self.proj is not None:
+            pooled = Fn.LinearFn.apply(pooled.contiguous(), self.proj, None, True)
+        return pooled
+
+    def _forward_tail_with_tokens(self, x: torch.Tensor):
+        """output_tokens=True (CoCa-style consumers): pooled features AND the token sequence, torch indexing."""
         if self.pool_style == "open_clip":
             pooled, tokens = self._global_pool(x)
             pooled = self.ln_post(pooled)
@@ -243,9 +267,7 @@ class VisionTransformer(nn.Module):
             raise ValueError(self.pool_style)
         if self.proj is not None:
             pooled = Fn.LinearFn.apply(pooled.contiguous(), self.proj, None, True)
-        if self.output_tokens:
-            return pooled, tokens
-        return pooled
+        return pooled, tokens
 
 
 class TextTransformer(nn.Module):
@@ -328,21 +350,20 @@ def text_tower_forward(mod, text: torch.Tensor, slice_positions: bool):
                          "(the reference adds the full positional embedding, model.py:247)")
     if L > mod.positional_embedding.shape[0]:
         raise ValueError(f"text length {L} exceeds the {mod.positional_embedding.shape[0]} positions of the tower")
-    x = mod.token_embedding(text).to(torch.bfloat16)
-    x = x + mod.positional_embedding[:L].to(torch.bfloat16)
+    x = Fn.EmbedTokensFn.apply(text, mod.token_embedding.weight, mod.positional_embedding)   # gather + positions
     W = x.shape[-1]
     causal = mod.attn_mask is not None
-    x = mod.transformer(x.reshape(N * L, W).contiguous(), N, L, causal=causal).reshape(N, L, W)
+    x = mod.transformer(x.reshape(N * L, W), N, L, causal=causal).reshape(N, L, W)
     # ln_final is row-wise, so normalising only the pooled rows equals model.py:251-254
     if mod.pool_style == 'open_clip':
-        pooled = x[torch.arange(N, device=x.device), text.argmax(dim=-1)]
+        pooled = Fn.PoolTokensFn.apply(x, POOL_ARGMAX_ID, text)       # EOT = first position of the largest id
     elif mod.pool_style == 'big_vision_tok':
-        pooled = x[:, 0]
+        pooled = Fn.PoolTokensFn.apply(x, POOL_FIRST, None)
     elif mod.pool_style == 'big_vision_last':
-        pooled = x[:, -1]
+        pooled = Fn.PoolTokensFn.apply(x, POOL_LAST, None)
     else:
         raise ValueError(mod.pool_style)
-    pooled = mod.ln_final(pooled.contiguous())
+    pooled = mod.ln_final(pooled)
     if mod.text_projection is not None:
         pooled = Fn.LinearFn.apply(pooled, mod.text_projection, None, True)
     return pooled

@@ -259,3 +259,116 @@ def adamw_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, e
                                           _ptr(param_bf16), n, lr, beta1, beta2, eps, weight_decay, step,
                                           grad_scale, _ptr(grad_scale_dev), int(zero_grad), _stream()),
               "clipa_adamw_step")
+
+
+# ------------------------------------------------------------------------------------------------
+# tower heads and tails (csrc/tower_io.cu)
+# ------------------------------------------------------------------------------------------------
+def preprocess_u8(images: torch.Tensor, mean, std) -> torch.Tensor:
+    """uint8 [n,3,H,W] (CUDA) -> normalised bf16, training/train.py:191-197."""
+    assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[1] == 3 and images.is_contiguous()
+    out = torch.empty(images.shape, dtype=torch.bfloat16, device=images.device)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    with _prof(("preprocess_u8",), 0.0, 3.0 * images.numel()):
+        check(_lib.lib().clipa_preprocess_u8(_ptr(images), _ptr(out), images.shape[0], images.shape[2], images.shape[3],
+                                             m, s, _stream()), "clipa_preprocess_u8")
+    return out
+
+
+def patchify(images: torch.Tensor, patch_h: int, patch_w: int, k_padded: int) -> torch.Tensor:
+    assert images.dim() == 4 and images.shape[1] == 3 and images.is_contiguous()
+    n, _, H, W = images.shape
+    rows = n * (H // patch_h) * (W // patch_w)
+    out = torch.empty(rows, k_padded, dtype=torch.bfloat16, device=images.device)
+    with _prof(("patchify",), 0.0, float(images.numel() * images.element_size() + 2 * out.numel())):
+        check(_lib.lib().clipa_patchify(_ptr(images), _dtype_code(images), _ptr(out), n, H, W, patch_h, patch_w, k_padded,
+                                        _stream()), "clipa_patchify")
+    return out
+
+
+def assemble_tokens(tok: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, n: int, L: int) -> torch.Tensor:
+    W = tok.shape[-1]
+    assert tok.dtype == torch.bfloat16 and tok.is_contiguous() and tok.numel() == n * (L - 1) * W
+    assert cls.dtype == torch.float32 and pos.dtype == torch.float32 and pos.is_contiguous() and pos.shape == (L, W)
+    x = torch.empty(n, L, W, dtype=torch.bfloat16, device=tok.device)
+    with _prof(("assemble_tokens",), 0.0, 4.0 * x.numel()):
+        check(_lib.lib().clipa_assemble_tokens(_ptr(tok), _ptr(cls), _ptr(pos), _ptr(x), n, L, W, _stream()),
+              "clipa_assemble_tokens")
+    return x
+
+
+def assemble_tokens_bwd(dx: torch.Tensor) -> torch.Tensor:
+    n, L, W = dx.shape
+    assert dx.dtype == torch.bfloat16 and dx.is_contiguous()
+    dtok = torch.empty(n * (L - 1), W, dtype=torch.bfloat16, device=dx.device)
+    with _prof(("assemble_tokens_bwd",), 0.0, 4.0 * dtok.numel()):
+        check(_lib.lib().clipa_assemble_tokens_bwd(_ptr(dx), _ptr(dtok), n, L, W, _stream()), "clipa_assemble_tokens_bwd")
+    return dtok
+
+
+def embed_tokens(ids: torch.Tensor, table: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    n, L = ids.shape
+    V, W = table.shape
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    assert table.dtype == torch.float32 and table.is_contiguous() and pos.dtype == torch.float32 and pos.is_contiguous()
+    assert pos.shape[0] >= L and pos.shape[1] == W
+    x = torch.empty(n, L, W, dtype=torch.bfloat16, device=table.device)
+    with _prof(("embed_tokens",), 0.0, 6.0 * x.numel()):
+        check(_lib.lib().clipa_embed_tokens(_ptr(ids), _ptr(table), _ptr(pos), _ptr(x), n, L, W, V, _stream()),
+              "clipa_embed_tokens")
+    return x
+
+
+def embed_tokens_bwd(ids: torch.Tensor, dx: torch.Tensor, dtable: torch.Tensor) -> None:
+    n, L = ids.shape
+    V, W = dtable.shape
+    assert dx.dtype == torch.bfloat16 and dx.is_contiguous() and dtable.dtype == torch.float32 and dtable.is_contiguous()
+    with _prof(("embed_tokens_bwd",), 0.0, 6.0 * dx.numel()):
+        check(_lib.lib().clipa_embed_tokens_bwd(_ptr(ids), _ptr(dx), _ptr(dtable), n, L, W, V, _stream()),
+              "clipa_embed_tokens_bwd")
+
+
+def pool_tokens(x: torch.Tensor, mode: int, ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n, L, W = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    if ids is not None:
+        assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.shape == (n, L)
+    out = torch.empty(n, W, dtype=torch.bfloat16, device=x.device)
+    with _prof(("pool_tokens", mode), 0.0, 2.0 * (x.numel() if mode >= 3 else out.numel()) + 2.0 * out.numel()):
+        check(_lib.lib().clipa_pool_tokens(_ptr(x), _ptr(ids), _ptr(out), n, L, W, mode, _stream()), "clipa_pool_tokens")
+    return out
+
+
+def pool_tokens_bwd(dout: torch.Tensor, mode: int, L: int, ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n, W = dout.shape
+    assert dout.dtype == torch.bfloat16 and dout.is_contiguous()
+    dx = torch.empty(n, L, W, dtype=torch.bfloat16, device=dout.device)
+    with _prof(("pool_tokens_bwd", mode), 0.0, 2.0 * dx.numel() + 2.0 * dout.numel()):
+        check(_lib.lib().clipa_pool_tokens_bwd(_ptr(dout), _ptr(ids), _ptr(dx), n, L, W, mode, _stream()),
+              "clipa_pool_tokens_bwd")
+    return dx
+
+
+def l2_normalize(x: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """Rows of x (bf16 [rows, E]) scaled to unit L2 norm; `out` may be a row-slice of a larger (gather) buffer."""
+    rows, E = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.dtype == torch.bfloat16 and out.shape == x.shape and out.stride(1) == 1
+    inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+    with _prof(("l2_normalize",), 0.0, 4.0 * x.numel()):
+        check(_lib.lib().clipa_l2_normalize(_ptr(x), _ptr(out), out.stride(0), _ptr(inv), rows, E, _stream()),
+              "clipa_l2_normalize")
+    return out, inv
+
+
+def l2_normalize_bwd(x: torch.Tensor, inv: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    rows, E = x.shape
+    assert dy.is_contiguous() and dy.shape == x.shape
+    dx = torch.empty_like(x)
+    with _prof(("l2_normalize_bwd",), 0.0, 6.0 * x.numel()):
+        check(_lib.lib().clipa_l2_normalize_bwd(_ptr(x), _ptr(inv), _ptr(dy), _dtype_code(dy), _ptr(dx), rows, E, _stream()),
+              "clipa_l2_normalize_bwd")
+    return dx

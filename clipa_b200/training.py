@@ -54,6 +54,7 @@ class TrainStep:
         self.device = dev
         mean = image_mean or getattr(model.visual, "image_mean", open_clip.factory.OPENAI_DATASET_MEAN)
         std = image_std or getattr(model.visual, "image_std", open_clip.factory.OPENAI_DATASET_STD)
+        self._mean_host, self._std_host = tuple(float(v) for v in mean), tuple(float(v) for v in std)
         self._mean = torch.tensor(mean, device=dev, dtype=torch.float32).reshape(1, 3, 1, 1)
         self._inv_std = (1.0 / torch.tensor(std, device=dev, dtype=torch.float32)).reshape(1, 3, 1, 1)
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
@@ -113,6 +114,9 @@ class TrainStep:
         """uint8 [B,3,H,W] (host or device) -> normalised bf16 on device (train.py:191-197)."""
         images = images.to(self.device, non_blocking=True)
         if images.dtype == torch.uint8:
+            if images.is_cuda and images.dim() == 4 and images.shape[1] == 3:
+                from . import ops
+                return ops.preprocess_u8(images.contiguous(), self._mean_host, self._std_host)   # one pass, own kernel
             images = (images.float().div_(255.0) - self._mean) * self._inv_std
         return images.to(torch.bfloat16)
 

@@ -167,6 +167,46 @@ int clipa_adamw_step(void* param, void* grad, void* exp_avg, void* exp_avg_sq, v
                      float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                      float grad_scale, const float* grad_scale_dev, int32_t zero_grad, void* stream);
 
+/* ---- tower heads and tails ("next" rows 8f.2 / 8f.4) ----------------------------------------------------
+ * The HBM-bound passes around the transformer blocks, one kernel each (forward and backward).
+ *
+ * clipa_preprocess_u8: images uint8 [n,3,H,W] -> bf16 (x/255 - mean[c]) / std[c]; h_mean3 / h_std3 are HOST
+ *   pointers to 3 floats.  Replaces `images.float().div(255)` + transforms.Normalize + cast of the
+ *   --to-float-on-device recipe, training/train.py:191-197.
+ * clipa_patchify: images (bf16 or f32, clipa_dtype) [n,3,H,W] -> patch rows bf16 [n*(H/ph)*(W/pw), k_padded],
+ *   element (c,py,px) of a patch at column c*ph*pw + py*pw + px, columns >= 3*ph*pw zero.  With
+ *   conv1.weight.reshape(width, 3*ph*pw) this turns the stride==kernel conv of VisionTransformer.forward
+ *   (open_clip/transformer.py:371,491-493) into one clipa_gemm.
+ * clipa_assemble_tokens: x[n,0,:] = cls + pos[0]; x[n,1+g,:] = tok[n*G+g,:] + pos[1+g,:]  (transformer.py:495-499);
+ *   tok bf16 [n*(L-1), W], cls f32 [W], pos f32 [L, W], x bf16 [n, L, W].  _bwd: dtok = dx[:,1:,:] (the cls / pos
+ *   gradients are column sums of dx: clipa_colsum_accum with ldx = L*W).
+ * clipa_embed_tokens: x[n,l,:] = table[ids[n,l],:] + pos[l,:] (open_clip/model.py:245-247); ids int64 [n,L],
+ *   table f32 [vocab, W], pos f32 [>=L, W].  _bwd: dtable[ids[n,l],:] += dx[n,l,:] (fp32 red.add).
+ * clipa_pool_tokens: out[n,:] = x[n,idx,:] with mode 0 first token (CLS, transformer.py:517), 1 last token
+ *   (big_vision_last), 2 first position of max(ids[n,:]) (EOT pooling, model.py:254), or the token mean with mode 3
+ *   (all tokens, transformer.py:515) / 4 (without the first, big_vision_gap :521-524).  _bwd writes the whole dx.
+ * clipa_l2_normalize: y = x / max(||x||_2, 1e-12) per row (F.normalize, model.py:240,263); y has row pitch ldy
+ *   so it can be the rank's slice of the all-gather buffer; inv_norm f32 [rows] is kept for _bwd:
+ *   dx = inv_norm * (dy - y (y.dy)), dy bf16 or f32. */
+int clipa_preprocess_u8(const void* images_u8, void* out_bf16, int64_t n, int32_t height, int32_t width,
+                        const float* h_mean3, const float* h_std3, void* stream);
+int clipa_patchify(const void* images, int32_t image_dtype, void* patches, int64_t n, int32_t height, int32_t width,
+                   int32_t patch_h, int32_t patch_w, int32_t k_padded, void* stream);
+int clipa_assemble_tokens(const void* tok, const float* cls, const float* pos, void* x, int64_t n, int32_t L,
+                          int32_t W, void* stream);
+int clipa_assemble_tokens_bwd(const void* dx, void* dtok, int64_t n, int32_t L, int32_t W, void* stream);
+int clipa_embed_tokens(const int64_t* ids, const float* table, const float* pos, void* x, int64_t n, int32_t L,
+                       int32_t W, int32_t vocab, void* stream);
+int clipa_embed_tokens_bwd(const int64_t* ids, const void* dx, float* dtable, int64_t n, int32_t L, int32_t W,
+                           int32_t vocab, void* stream);
+int clipa_pool_tokens(const void* x, const int64_t* ids, void* out, int64_t n, int32_t L, int32_t W, int32_t mode,
+                      void* stream);
+int clipa_pool_tokens_bwd(const void* dout, const int64_t* ids, void* dx, int64_t n, int32_t L, int32_t W,
+                          int32_t mode, void* stream);
+int clipa_l2_normalize(const void* x, void* y, int64_t ldy, float* inv_norm, int64_t rows, int32_t E, void* stream);
+int clipa_l2_normalize_bwd(const void* x, const float* inv_norm, const void* dy, int32_t dy_dtype, void* dx,
+                           int64_t rows, int32_t E, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -319,3 +319,93 @@ def test_fused_adamw_matches_torch(dev, wd):
         assert torch.count_nonzero(gbuf).item() == 0
     assert relmax(p, ref.detach()) < 1e-6
     assert torch.equal(shadow, p.bfloat16())
+
+
+# ---- tower heads and tails (csrc/tower_io.cu) against the torch expressions the reference uses ------------------
+def test_preprocess_u8_matches_reference_recipe(dev):
+    """training/train.py:191-197: images.float().div(255) -> Normalize(mean, std) -> cast."""
+    o = ops()
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    for (n, h, w) in ((3, 126, 126), (2, 7, 9), (1, 224, 224)):
+        img = torch.randint(0, 256, (n, 3, h, w), dtype=torch.uint8, device=dev)
+        got = o.preprocess_u8(img, mean, std)
+        m = torch.tensor(mean, device=dev).view(1, 3, 1, 1)
+        s = torch.tensor(std, device=dev).view(1, 3, 1, 1)
+        ref = ((img.float().div(255) - m) / s)
+        assert got.dtype == torch.bfloat16 and relmax(got, ref) < 4e-3
+
+
+@pytest.mark.parametrize("n,size,patch,width", [(3, 126, 14, 64), (2, 64, 16, 128), (2, 96, 32, 32)])
+def test_patchify_plus_gemm_equals_conv(dev, n, size, patch, width):
+    """conv1 with stride == kernel (open_clip/transformer.py:371,491-493) == patchify + GEMM."""
+    o = ops()
+    torch.manual_seed(n + size)
+    img = torch.randn(n, 3, size, size, device=dev)
+    wgt = torch.randn(width, 3, patch, patch, device=dev) * 0.05
+    K = 3 * patch * patch
+    Kp = (K + 7) // 8 * 8
+    for x in (img, img.bfloat16()):
+        p = o.patchify(x.contiguous(), patch, patch, Kp)
+        assert p.shape == (n * (size // patch) ** 2, Kp) and (p[:, K:] == 0).all()
+        ref = torch.nn.functional.conv2d(x.float().bfloat16().float(), wgt.bfloat16().float(), stride=patch)
+        ref = ref.reshape(n, width, -1).permute(0, 2, 1).reshape(-1, width)
+        got = p[:, :K].float() @ wgt.reshape(width, K).bfloat16().float().t()
+        assert relmax(got, ref) < 1e-3
+
+
+def test_assemble_embed_pool_normalize_match_torch(dev):
+    from clipa_b200 import functional as Fn
+    from clipa_b200._lib import POOL_ARGMAX_ID, POOL_FIRST, POOL_LAST, POOL_MEAN_ALL, POOL_MEAN_SKIP_FIRST
+    torch.manual_seed(0)
+    n, L, W, V = 5, 10, 64, 97
+    # [cls; tok] + pos, forward and backward (learnable table and fixed table)
+    tok = mk((n * (L - 1), W), dev).requires_grad_(True)
+    cls = torch.randn(W, device=dev, requires_grad=True)
+    for learn in (True, False):
+        pos = torch.randn(L, W, device=dev, requires_grad=learn)
+        x = Fn.AssembleTokensFn.apply(tok, cls, pos, n, L)
+        ref = torch.cat([cls.expand(n, 1, W), tok.float().reshape(n, L - 1, W)], 1) + pos
+        assert relmax(x, ref) < BF16_OUT
+        g = mk((n, L, W), dev)
+        gt, gc, gp = torch.autograd.grad(x, [tok, cls] + ([pos] if learn else []), g) + ((None,) if not learn else ())
+        rt, rc, rp = torch.autograd.grad(ref, [tok, cls] + ([pos] if learn else []), g.float()) + ((None,) if not learn else ())
+        assert relmax(gt, rt) < 1e-6 and relmax(gc, rc) < 1e-5
+        if learn:
+            assert relmax(gp, rp) < 1e-5
+    # token embedding gather + positions
+    ids = torch.randint(0, V, (n, L), device=dev)
+    table = torch.randn(V, W, device=dev, requires_grad=True)
+    pos = torch.randn(L + 3, W, device=dev, requires_grad=True)
+    x = Fn.EmbedTokensFn.apply(ids, table, pos)
+    ref = table[ids] + pos[:L]
+    assert relmax(x, ref) < BF16_OUT
+    g = mk((n, L, W), dev)
+    gt, gp = torch.autograd.grad(x, [table, pos], g)
+    rt, rp = torch.autograd.grad(ref, [table, pos], g.float())
+    assert relmax(gt, rt) < 1e-5 and relmax(gp, rp) < 1e-5
+    # pooling modes
+    xx = mk((n, L, W), dev).requires_grad_(True)
+    refs = {POOL_FIRST: lambda t: t[:, 0], POOL_LAST: lambda t: t[:, -1],
+            POOL_ARGMAX_ID: lambda t: t[torch.arange(n, device=dev), ids.argmax(-1)],
+            POOL_MEAN_ALL: lambda t: t.mean(1), POOL_MEAN_SKIP_FIRST: lambda t: t[:, 1:].mean(1)}
+    for mode, fn in refs.items():
+        y = Fn.PoolTokensFn.apply(xx, mode, ids if mode == POOL_ARGMAX_ID else None)
+        r = fn(xx.float())
+        assert relmax(y, r) < BF16_OUT
+        g = mk((n, W), dev)
+        assert relmax(torch.autograd.grad(y, xx, g)[0], torch.autograd.grad(r, xx, g.float())[0]) < BF16_OUT
+    # ties in the ids: torch.argmax returns the FIRST maximal position
+    tie = torch.zeros(n, L, dtype=torch.int64, device=dev)
+    tie[:, 3] = 7; tie[:, 6] = 7
+    assert torch.equal(Fn.PoolTokensFn.apply(xx, POOL_ARGMAX_ID, tie), xx[:, 3].detach())
+    # F.normalize and its backward; output written into a slice of a wider buffer
+    f = mk((33, 128), dev).requires_grad_(True)
+    y = Fn.L2NormalizeFn.apply(f, None)
+    r = torch.nn.functional.normalize(f.float(), dim=-1)
+    assert relmax(y, r) < BF16_OUT
+    g = torch.randn(33, 128, device=dev)
+    assert relmax(torch.autograd.grad(y, f, g)[0], torch.autograd.grad(r, f, g)[0]) < 2e-2
+    buf = torch.zeros(99, 128, dtype=torch.bfloat16, device=dev)
+    y2 = Fn.L2NormalizeFn.apply(f, buf[33:66])
+    assert torch.equal(buf[33:66], y.detach()) and (buf[:33] == 0).all() and (buf[66:] == 0).all()
+    assert y2.data_ptr() == buf[33:66].data_ptr()

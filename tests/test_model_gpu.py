@@ -250,21 +250,25 @@ def test_fused_train_step_matches_torch_optimizer_step(dev):
 @pytest.mark.parametrize("micro", [4, 5, 8])
 def test_gradcache_chunks_match_single_pass(dev, micro):
     """TrainStep's GradCache schedule (train.py:216-256; ragged last chunk, last chunk's graph kept) gives the
-    same loss and parameter gradients as one pass over the whole batch."""
+    same loss and parameter gradients as one pass over the whole batch -- except logit_scale, whose gradient the
+    reference's accumulation loop counts once per chunk (reproduced by default, tests/test_host_logic_cpu.py)."""
     from clipa_b200.training import TrainStep
     from oracle.weights import make_inputs
     meta, _ = load_golden("tiny-cls", "fp32")
     images, text = make_inputs(meta["cfg"], 16, 5, image_size=meta["image_size"])
     out = []
-    for mb in (16, micro):
+    for mb, quirk in ((16, True), (micro, False), (micro, True)):
         model = build_model(meta, "amp_bf16", dev)
-        ts = TrainStep(model, micro_batch=mb, lr=1e-3)
+        ts = TrainStep(model, micro_batch=mb, lr=1e-3, reference_accum_logit_scale=quirk)
         loss = ts.forward_backward(ts.preprocess(images), text.to(dev))
         out.append((loss.item(), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}))
-    (l0, g0), (l1, g1) = out
+    (l0, g0), (l1, g1), (l2, g2) = out
     assert abs(l0 - l1) / abs(l0) < 2e-3, (l0, l1)       # features are bf16 either way; chunking changes GEMM tiling only
     for n in g0:
         assert rel_err(g1[n].cpu(), g0[n].cpu()) < 2e-2, n
+    n_chunks = -(-16 // micro)
+    assert rel_err(g2["logit_scale"].cpu(), n_chunks * g0["logit_scale"].cpu()) < 2e-2
+    assert rel_err(g2["visual.proj"].cpu(), g0["visual.proj"].cpu()) < 2e-2
 
 
 def test_patch_dropout_runs_on_device(dev):
