@@ -270,7 +270,8 @@ def main():
     from clipa_b200.open_clip.transformer import Transformer as _T
     _T.save_ln_outputs = {"auto": "auto", "on": True, "off": False}[args.save_ln]
     model.train()
-    trainer = TrainStep(model, rank=rank, world_size=world, micro_batch=args.micro_batch)
+    trainer = TrainStep(model, rank=rank, world_size=world, micro_batch=args.micro_batch,
+                        overlap_grad_allreduce=os.environ.get("CLIPA_OVERLAP", "1") != "0")
     ctx = model.context_length
     vocab = model.vocab_size
     g = torch.Generator().manual_seed(1 + rank)

@@ -19,6 +19,7 @@ from . import ops
 from ._lib import EPI_ATOMIC_F32, EPI_BIAS_ACT, EPI_DACT, EPI_STORE
 
 _BF16 = torch.bfloat16
+P_TILDE_BYTES = 512 << 20      # cap of one materialised softmax-gradient block of the contrastive head (per direction)
 
 
 def compute_copy(p: torch.Tensor) -> torch.Tensor:
@@ -260,21 +261,33 @@ class ClipLossFn(torch.autograd.Function):
         ctx.has_grads = any(ctx.needs_input_grad[:5])
         if not ctx.has_grads:          # eval / torch.no_grad(): no backward will follow
             return loss
-        # gradients (scaled by grad_output in backward); P~ tiles are stored pre-multiplied by the scale
+        # gradients (scaled by grad_output in backward).  P~ = softmax - onehot is materialised in bf16, pre-multiplied
+        # by the scale, one COLUMN BLOCK of the gathered batch at a time (<= P_TILDE_BYTES per direction; the whole
+        # [B_local x B_global] matrix would be 2 x 1 GiB per GPU at B_global = 65 536): d(local) accumulates over the
+        # blocks through the fp32 red.add epilogue, d(gathered) rows of a block are written once.
         ds = torch.zeros(1, dtype=torch.float32, device=dev)
         c = 0.5 / bl
-        p_i = ops.clip_softmax_grad(img, atxt, s_dev, off, lse_i, ds, scale_output=True)   # s * Pi  [bl, bg] bf16
-        p_t = ops.clip_softmax_grad(txt, aimg, s_dev, off, lse_t, ds, scale_output=True)
-        d_img = torch.empty(bl, E, dtype=torch.float32, device=dev)
-        d_txt = torch.empty(bl, E, dtype=torch.float32, device=dev)
-        ops.gemm(p_i, atxt.t(), d_img, alpha=c)                     # dI = c*s * Pi @ T_all
-        ops.gemm(p_t, aimg.t(), d_txt, alpha=c)                     # dT = c*s * Pt @ I_all
+        want_all = need_all_grads and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        cb = bg if bl * bg * 2 <= P_TILDE_BYTES else max(1024, (P_TILDE_BYTES // (2 * bl)) // 256 * 256)
+        chunked = cb < bg
+        d_img = (torch.zeros if chunked else torch.empty)(bl, E, dtype=torch.float32, device=dev)
+        d_txt = (torch.zeros if chunked else torch.empty)(bl, E, dtype=torch.float32, device=dev)
         d_all_img = d_all_txt = None
-        if need_all_grads and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
+        if want_all:
             d_all_txt = torch.empty(bg, E, dtype=torch.float32, device=dev)
             d_all_img = torch.empty(bg, E, dtype=torch.float32, device=dev)
-            ops.gemm(p_i.t(), img.t(), d_all_txt, alpha=c)          # dT_all = c*s * Pi^T @ I
-            ops.gemm(p_t.t(), txt.t(), d_all_img, alpha=c)          # dI_all = c*s * Pt^T @ T
+        epi = EPI_ATOMIC_F32 if chunked else EPI_STORE
+        for c0 in range(0, bg, cb):
+            c1 = min(bg, c0 + cb)
+            t_blk, i_blk = atxt[c0:c1], aimg[c0:c1]
+            p_i = ops.clip_softmax_grad(img, t_blk, s_dev, off - c0, lse_i, ds, scale_output=True)   # s * Pi[:, c0:c1]
+            p_t = ops.clip_softmax_grad(txt, i_blk, s_dev, off - c0, lse_t, ds, scale_output=True)
+            ops.gemm(p_i, t_blk.t(), d_img, alpha=c, epilogue=epi, split_k=1)  # dI (+)= c*s * Pi @ T_all[block]
+            ops.gemm(p_t, i_blk.t(), d_txt, alpha=c, epilogue=epi, split_k=1)  # dT (+)= c*s * Pt @ I_all[block]
+            if want_all:
+                ops.gemm(p_i.t(), img.t(), d_all_txt[c0:c1], alpha=c)         # dT_all[block] = c*s * Pi^T @ I
+                ops.gemm(p_t.t(), txt.t(), d_all_img[c0:c1], alpha=c)         # dI_all[block] = c*s * Pt^T @ T
+            del p_i, p_t
         ctx.save_for_backward(d_img, d_txt, d_all_img, d_all_txt, ds * c)
         ctx.dtypes = (image_features.dtype, logit_scale.dtype)
         return loss

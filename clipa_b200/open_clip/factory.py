@@ -153,6 +153,12 @@ def create_model_and_transforms(model_name: str, pretrained: Optional[str] = Non
     return model, preprocess_train, preprocess_val
 
 
+def trace_model(model, batch_size=256, device=torch.device('cpu')):
+    """open_clip/factory.py (imported by training/main.py:40): torch.jit tracing does not apply to custom CUDA autograd
+    nodes."""
+    raise NotImplementedError("trace_model: torch.jit tracing is not applicable to the custom-kernel towers")
+
+
 def get_tokenizer(model_name):
     raise NotImplementedError("tokenizers are host-side string processing outside the hot path; the model "
                               "consumes int64 token ids [batch, context_length] from the reference tokenizer")

@@ -101,6 +101,17 @@ class ResidualAttentionBlock(nn.Module):
             batch, seq, self.n_head, causal, self.act, save_ln)
 
 
+class _GradReady:
+    """Tensor hook: reports, does not touch the gradient."""
+
+    def __init__(self, cb, tower, index):
+        self.cb, self.tower, self.index = cb, tower, index
+
+    def __call__(self, grad):
+        self.cb(self.tower, self.index)
+        return None
+
+
 class Transformer(nn.Module):
     """open_clip/transformer.py:294-326.  `grad_checkpointing` is accepted for API parity; the block
     function already recomputes its MLP activations, so the flag does not change the math."""
@@ -133,9 +144,17 @@ class Transformer(nn.Module):
         free += torch.cuda.memory_reserved(x.device) - torch.cuda.memory_allocated(x.device)
         return need + (16 << 30) < free                # keep a 16 GB margin for the other tower / head
 
+    # TrainStep's overlapped gradient all-reduce: callback(tower, i) fires in backward once the gradients of every
+    # block >= i are complete (tensor hook on the input of block i), for i = 0, k, 2k, ...
+    grad_ready_callback = None
+    grad_bucket_blocks = 4
+
     def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool = False):
         save_ln = self._decide_save_ln(x)
-        for r in self.resblocks:
+        cb = self.grad_ready_callback if torch.is_grad_enabled() else None
+        for i, r in enumerate(self.resblocks):
+            if cb is not None and x.requires_grad and i % self.grad_bucket_blocks == 0:
+                x.register_hook(_GradReady(cb, self, i))
             x = r(x, batch, seq, causal, save_ln)
         return x
 

@@ -19,6 +19,7 @@ weights + gradient clear + 1/world_size averaging in one pass).
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Optional, Tuple
 
@@ -34,12 +35,15 @@ def exclude_from_wd(name: str, p: torch.Tensor) -> bool:
 
 
 class TrainStep:
+    _armed = False          # overlapped all-reduce in flight for the current backward (see _setup_overlap)
+
     def __init__(self, model: torch.nn.Module, *, rank: int = 0, world_size: int = 1,
                  lr: float = 1.024e-3, betas: Tuple[float, float] = (0.9, 0.95), eps: float = 1e-6,
                  wd: float = 0.2, micro_batch: int = 4096, local_loss: bool = True,
                  gather_with_grad: bool = True, image_mean=None, image_std=None,
                  grad_clip_norm: Optional[float] = None, fused_optimizer: bool = True,
-                 reference_accum_logit_scale: bool = True):
+                 reference_accum_logit_scale: bool = True, overlap_grad_allreduce: bool = True,
+                 allreduce_bucket_blocks: int = 4):
         self.model = model
         self.rank, self.world_size = rank, world_size
         self.micro_batch = micro_batch
@@ -48,6 +52,10 @@ class TrainStep:
         # logit_scale gradient is accumulated accum_freq times (tower parameters are not: chunk j only reaches
         # them through its own features).  Reproduced by default; False gives the single-pass gradient.
         self.reference_accum_logit_scale = reference_accum_logit_scale
+        self.overlap = overlap_grad_allreduce and world_size > 1
+        self._bucket_blocks = allreduce_bucket_blocks
+        self._armed = False
+        self._works, self._done_ranges = [], []
         self.loss_fn = open_clip.ClipLoss(local_loss=local_loss, gather_with_grad=gather_with_grad,
                                           cache_labels=True, rank=rank, world_size=world_size)
         dev = next(model.parameters()).device
@@ -72,6 +80,7 @@ class TrainStep:
             # so one optimizer step is two launches of clipa_adamw_step and the data-parallel
             # gradient reduction is one all-reduce per group.
             self._groups = []
+            self._param_slot = {}          # id(param) -> (group index, offset, numel) in the flat buffers
             for ps, group_wd in ((gain, 0.0), (rest, wd)):
                 if not ps:
                     continue
@@ -90,6 +99,7 @@ class TrainStep:
                     shadow = fb[off:off + n].view_as(p)
                     shadow.copy_(p.data)
                     p._clipa_bf16 = (p._version, shadow)
+                    self._param_slot[id(p)] = (len(self._groups), off, n)
                     off += sz
                 self._groups.append(dict(p=fp, g=fg, m=torch.zeros_like(fp), v=torch.zeros_like(fp), b=fb, wd=group_wd,
                                          params=ps, sizes=sizes))
@@ -109,6 +119,68 @@ class TrainStep:
                 [{"params": gain, "weight_decay": 0.}, {"params": rest, "weight_decay": wd}],
                 lr=lr, betas=betas, eps=eps, fused=dev.type == "cuda")
 
+    # ---- gradient all-reduce overlapped with backward (the role of DDP's buckets, training/main.py:299) ----------
+    # Gradients land directly in the flat buffers, and a tower's blocks finish their backward last-to-first, so a
+    # bucket of `allreduce_bucket_blocks` consecutive blocks is one contiguous range per weight-decay group that is
+    # complete as soon as d(input of its first block) has been computed.  Transformer.forward puts a tensor hook
+    # there; the hook launches the NCCL all-reduce of the range on a side stream while the earlier blocks are
+    # still back-propagating.  What no bucket covers (embeddings, projections, ln_pre/post, logit_scale) is reduced
+    # after backward.  Every rank builds the same graph, so the hooks fire -- and the collectives are issued -- in
+    # the same order everywhere.
+    def _setup_overlap(self):
+        self._buckets = {}
+        towers = []
+        for mod in self.model.modules():
+            if type(mod).__name__ == "Transformer" and hasattr(mod, "resblocks"):
+                towers.append(mod)
+        for tower in towers:
+            blocks = list(tower.resblocks)
+            for b0 in range(0, len(blocks), self._bucket_blocks):
+                ranges = {}
+                for blk in blocks[b0:b0 + self._bucket_blocks]:
+                    for p in blk.parameters():
+                        slot = self._param_slot.get(id(p))
+                        if slot is None:
+                            continue
+                        gi, off, n = slot
+                        lo, hi = ranges.get(gi, (1 << 62, 0))
+                        ranges[gi] = (min(lo, off), max(hi, off + n))
+                if ranges:
+                    self._buckets[(id(tower), b0)] = [(gi, lo, hi) for gi, (lo, hi) in sorted(ranges.items())]
+            tower.grad_bucket_blocks = self._bucket_blocks
+            tower.grad_ready_callback = self._on_blocks_ready
+        self._side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+
+    def _on_blocks_ready(self, tower, first_block: int):
+        """Called from the autograd engine when every block >= first_block of `tower` has its gradients."""
+        if not self._armed:
+            return
+        ranges = self._buckets.get((id(tower), first_block))
+        if not ranges:
+            return
+        if self._side is not None:
+            ev = torch.cuda.Event()
+            ev.record()                               # the wgrads / reductions of these blocks are in flight before it
+            self._side.wait_event(ev)
+        with (torch.cuda.stream(self._side) if self._side is not None else contextlib.nullcontext()):
+            for gi, lo, hi in ranges:
+                self._works.append(dist.all_reduce(self._groups[gi]["g"][lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+                self._done_ranges.append((gi, lo, hi))
+
+    def _finish_overlapped_allreduce(self):
+        """All-reduce whatever the buckets did not cover, then make the compute stream wait for all of it."""
+        for gi, grp in enumerate(self._groups):
+            done = sorted((lo, hi) for g, lo, hi in self._done_ranges if g == gi)
+            pos, total = 0, grp["g"].numel()
+            for lo, hi in done + [(total, total)]:
+                if lo > pos:
+                    self._works.append(dist.all_reduce(grp["g"][pos:lo], op=dist.ReduceOp.SUM, async_op=True))
+                pos = max(pos, hi)
+        for w in self._works:
+            w.wait()
+        self._works, self._done_ranges = [], []
+        self._armed = False
+
     # -------------------------------------------------------------------------------------
     def preprocess(self, images: torch.Tensor) -> torch.Tensor:
         """uint8 [B,3,H,W] (host or device) -> normalised bf16 on device (train.py:191-197)."""
@@ -126,9 +198,13 @@ class TrainStep:
 
     def _allreduce_grads(self, average: bool = True):
         if self.world_size > 1:
-            for flat in self._flat.values():
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-                if average:
+            if self._armed:                 # buckets were launched during backward: reduce the rest and wait
+                self._finish_overlapped_allreduce()
+            else:
+                for flat in self._flat.values():
+                    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            if average:
+                for flat in self._flat.values():
                     flat.div_(self.world_size)
 
     def optimizer_step(self, grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None):
@@ -198,10 +274,14 @@ class TrainStep:
         model = self.model
         B = images.shape[0]
         mb = self.micro_batch
+        overlap = self.overlap and self.fused
+        if overlap and not hasattr(self, "_buckets"):
+            self._setup_overlap()
         if B <= mb:
             out = model(images, texts)
             feats_i, feats_t, scale = self._unpack(out)
             loss = self.loss_fn(feats_i, feats_t, scale)
+            self._armed = overlap            # this backward completes the gradients: buckets may go out as they finish
             loss.backward()
             return loss.detach()
         chunks = [(s, min(B, s + mb)) for s in range(0, B, mb)]
@@ -240,6 +320,7 @@ class TrainStep:
             if stochastic:
                 torch.cuda.set_rng_state(rng[c], self.device)
             a, b, _ = self._unpack(model(images[s:e], texts[s:e]))
+            self._armed = overlap and c == len(chunks) - 2      # the LAST backward completes the accumulated gradients
             torch.autograd.backward([a, b], [fi.grad[s:e], ft.grad[s:e]])
         if stochastic:
             torch.cuda.set_rng_state(after, self.device)

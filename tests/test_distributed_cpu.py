@@ -57,6 +57,27 @@ def _worker(rank, world, port, out_dir):
         flat.fill_(float(rank + 1))
         ts._allreduce_grads()
         ok = ok and torch.allclose(lin.weight.grad, torch.full((3, 4), 1.5)) and torch.allclose(lin.bias.grad, torch.full((3,), 1.5))
+        # bucketed (overlapped) all-reduce bookkeeping of TrainStep: ranges reduced by the block hooks + the complement
+        # reduced after backward cover every element exactly once
+        from clipa_b200.open_clip.transformer import Transformer
+        net = torch.nn.Module()
+        net.visual = torch.nn.Linear(8, 8)              # not in any bucket: reduced by the complement pass
+        net.transformer = Transformer(width=64, layers=5, heads=1)
+        net.logit_scale = torch.nn.Parameter(torch.tensor(1.0))
+        ts2 = TrainStep(net, rank=rank, world_size=world, micro_batch=4, image_mean=(0., 0., 0.), image_std=(1., 1., 1.),
+                        allreduce_bucket_blocks=2)
+        assert ts2.fused and ts2.overlap
+        ts2._setup_overlap()
+        assert sorted(b0 for (_, b0) in ts2._buckets) == [0, 2, 4]
+        for grp in ts2._groups:
+            grp["g"].fill_(float(rank + 1))
+        ts2._armed = True
+        for b0 in (4, 2):                                # backward order: last blocks first; bucket 0 never fires here
+            ts2._on_blocks_ready(net.transformer, b0)
+        covered = sum(hi - lo for _, lo, hi in ts2._done_ranges)
+        assert 0 < covered < sum(g["g"].numel() for g in ts2._groups)
+        ts2._allreduce_grads(average=True)
+        ok = ok and all(torch.allclose(g["g"], torch.full_like(g["g"], 1.5)) for g in ts2._groups) and not ts2._armed
         with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
             f.write("1" if ok else "0")
     finally:

@@ -409,3 +409,29 @@ def test_assemble_embed_pool_normalize_match_torch(dev):
     y2 = Fn.L2NormalizeFn.apply(f, buf[33:66])
     assert torch.equal(buf[33:66], y.detach()) and (buf[:33] == 0).all() and (buf[66:] == 0).all()
     assert y2.data_ptr() == buf[33:66].data_ptr()
+
+
+def test_clip_loss_column_chunking_matches_unchunked(dev, monkeypatch):
+    """The head materialises its softmax-gradient matrix one column block at a time once it would exceed
+    functional.P_TILDE_BYTES (config 5: 2 x 1 GiB per GPU otherwise); same loss and gradients as the one-block path."""
+    from clipa_b200 import functional as Fn
+    from clipa_b200.open_clip import ClipLoss
+    torch.manual_seed(4)
+    bl, bg, E = 512, 4096, 256
+    a = torch.nn.functional.normalize(torch.randn(bl, E, device=dev), dim=-1).bfloat16()
+    b = torch.nn.functional.normalize(torch.randn(bl, E, device=dev), dim=-1).bfloat16()
+    a_all = torch.nn.functional.normalize(torch.randn(bg, E, device=dev), dim=-1).bfloat16()
+    b_all = torch.nn.functional.normalize(torch.randn(bg, E, device=dev), dim=-1).bfloat16()
+    a_all[1024:1024 + bl], b_all[1024:1024 + bl] = a, b           # this rank's rows sit at offset 1024 (rank 2 of 8)
+    scale = torch.tensor(14.285714, device=dev, requires_grad=True)
+    res = []
+    for cap in (1 << 40, 2 * bl * 1024):                           # one block / four column blocks of 1024
+        monkeypatch.setattr(Fn, "P_TILDE_BYTES", cap)
+        ins = [t.clone().requires_grad_(True) for t in (a, b, a_all, b_all)]
+        loss = Fn.ClipLossFn.apply(ins[0], ins[1], ins[2], ins[3], scale, 2, True)
+        grads = torch.autograd.grad(loss, ins + [scale])
+        res.append((loss.item(), grads))
+    (l0, g0), (l1, g1) = res
+    assert abs(l0 - l1) < 1e-6
+    for x, y in zip(g0, g1):
+        assert relmax(y, x) < 2e-3        # fp32 accumulation order differs between the two paths
