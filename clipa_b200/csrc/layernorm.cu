@@ -179,13 +179,17 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 // reduces them through shared memory and issues one red.add per column per block.  The row is
 // held PACKED (bf16x2) between the statistics pass and the output pass and gamma is read from
 // shared memory; one 12-warp block per SM gives each thread 170 registers (64 of them partials).
-template <int VPL, bool FULL>
+// DXS: also accumulate the column sums of the OUTPUT dx into dxsum -- the bias gradient of the Linear layer
+// whose output this LayerNorm's input stream received (d b_out = colsum(dx1), d b_proj of the previous block =
+// colsum(dx)): the standalone column-sum pass over a tensor this kernel has just produced disappears.  The sums
+// are kept per warp in shared memory (split float4 halves, conflict-free), not in registers.
+template <int VPL, bool FULL, bool DXS>
 __global__ void __launch_bounds__(kLnBwdWarps * 32, 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const float* __restrict__ gamma, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
               __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              long long rows, int D) {
+              float* __restrict__ dxsum, long long rows, int D) {
   extern __shared__ float4 ln_smem4[];  // gamma (split halves), then [kLnBwdWarps][2][D] reduction scratch
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -193,11 +197,20 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   float4* g_lo = ln_smem4;
   float4* g_hi = g_lo + nvec;
   float* scratch = reinterpret_cast<float*>(g_hi + nvec);
+  // [kLnBwdWarps][2][D] reduction scratch, then (DXS) [kLnBwdWarps][D] dx column sums as lo / hi float4 halves
+  float4* sx_lo = reinterpret_cast<float4*>(scratch + (size_t)kLnBwdWarps * 2 * D) + (size_t)warp * 2 * nvec;
+  float4* sx_hi = sx_lo + nvec;
   const long long warp_global = (long long)blockIdx.x * kLnBwdWarps + warp;
   const long long warp_stride = (long long)gridDim.x * kLnBwdWarps;
   const float inv_d = 1.0f / (float)D;
 
   stage_param(g_lo, g_hi, gamma, nvec);
+  if (DXS) {
+    for (int vi = lane; vi < nvec; vi += 32) {
+      sx_lo[vi] = make_float4(0.f, 0.f, 0.f, 0.f);
+      sx_hi[vi] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   __syncthreads();
 
   float2 acc_g[VPL][4], acc_b[VPL][4];
@@ -280,6 +293,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
           for (int j = 0; j < 4; ++j) o[j] = add2(o[j], r[j]);
         }
         dxr[vi] = pack8p(o);
+        if (DXS) {
+          float4 a = sx_lo[vi], b = sx_hi[vi];
+          a.x += o[0].x; a.y += o[0].y; a.z += o[1].x; a.w += o[1].y;
+          b.x += o[2].x; b.y += o[2].y; b.z += o[3].x; b.w += o[3].y;
+          sx_lo[vi] = a;
+          sx_hi[vi] = b;
+        }
       }
     }
   }
@@ -308,6 +328,15 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     }
     atomicAdd(dgamma + c, sg);
     atomicAdd(dbeta + c, sb);
+    if (DXS) {
+      const float* sx = scratch + (size_t)kLnBwdWarps * 2 * D;
+      const int vi = c >> 3, r = c & 7;
+      const int idx = r < 4 ? vi * 4 + r : nvec * 4 + vi * 4 + (r - 4);
+      float sd = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLnBwdWarps; ++w) sd += sx[(size_t)w * D + idx];
+      atomicAdd(dxsum + c, sd);
+    }
   }
 }
 
@@ -362,23 +391,31 @@ static int launch_ln_fwd(const void* x, const void* gamma, const void* beta, voi
   return CLIPA_OK;
 }
 
+int colsum_launch(const void* x, long long ldx, float* out, long long rows, int N, cudaStream_t s);
+
 template <int VPL>
 static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
                          const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
-                         long long rows, int D, cudaStream_t s) {
+                         float* dxsum, long long rows, int D, cudaStream_t s) {
   long long blocks = (rows + kLnBwdWarps - 1) / kLnBwdWarps;
   const long long cap = (long long)num_sms();
   if (blocks > cap) blocks = cap;
-  const size_t smem = ((size_t)kLnBwdWarps * 2 + 1) * D * sizeof(float);
-  auto kern = (D == 256 * VPL) ? ln_bwd_kernel<VPL, true> : ln_bwd_kernel<VPL, false>;
+  size_t smem = ((size_t)kLnBwdWarps * 2 + 1) * D * sizeof(float);
+  const size_t smem_dxs = smem + (size_t)kLnBwdWarps * D * sizeof(float);
+  const bool fuse = dxsum != nullptr && smem_dxs <= 227 * 1024;   // very wide rows: separate column-sum pass below
+  if (fuse) smem = smem_dxs;
+  const bool full = D == 256 * VPL;
+  auto kern = fuse ? (full ? ln_bwd_kernel<VPL, true, true> : ln_bwd_kernel<VPL, false, true>)
+                   : (full ? ln_bwd_kernel<VPL, true, false> : ln_bwd_kernel<VPL, false, false>);
   if (smem > 48 * 1024)
     CLIPA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, kLnBwdWarps * 32, smem, s>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
       static_cast<const float*>(gamma), mean, rstd, static_cast<const __nv_bfloat16*>(dres),
-      static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, D);
+      static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, dxsum, rows, D);
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
+  if (dxsum != nullptr && !fuse) return colsum_launch(dx, D, dxsum, rows, D, s);
   return CLIPA_OK;
 }
 
@@ -409,7 +446,7 @@ extern "C" int clipa_layernorm_fwd(const void* x, const void* gamma, const void*
 
 extern "C" int clipa_layernorm_bwd(const void* dy, const void* x, const void* gamma,
                                    const float* mean, const float* rstd, const void* dres, void* dx,
-                                   float* dgamma, float* dbeta, int64_t rows, int32_t D,
+                                   float* dgamma, float* dbeta, float* dxsum, int64_t rows, int32_t D,
                                    void* stream) {
   CLIPA_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, CLIPA_ERR_BAD_ARG,
                 "layernorm_bwd: null pointer");
@@ -419,12 +456,12 @@ extern "C" int clipa_layernorm_bwd(const void* dy, const void* x, const void* ga
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int vpl = (D / 8 + 31) / 32;
   switch (vpl) {
-    case 1: return launch_ln_bwd<1>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D, s);
-    case 2: return launch_ln_bwd<2>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D, s);
-    case 3: return launch_ln_bwd<3>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D, s);
-    case 4: return launch_ln_bwd<4>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D, s);
-    case 5: return launch_ln_bwd<5>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D, s);
-    default: return launch_ln_bwd<8>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D, s);
+    case 1: return launch_ln_bwd<1>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D, s);
+    case 2: return launch_ln_bwd<2>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D, s);
+    case 3: return launch_ln_bwd<3>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D, s);
+    case 4: return launch_ln_bwd<4>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D, s);
+    case 5: return launch_ln_bwd<5>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D, s);
+    default: return launch_ln_bwd<8>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dxsum, rows, D, s);
   }
 }
 
@@ -433,6 +470,10 @@ extern "C" int clipa_colsum_accum(const void* x, int64_t ldx, float* out, int64_
   CLIPA_REQUIRE(x && out, CLIPA_ERR_BAD_ARG, "colsum: null pointer");
   CLIPA_REQUIRE(rows > 0 && N > 0 && N % 8 == 0 && ldx % 8 == 0, CLIPA_ERR_UNSUPPORTED,
                 "colsum: need N %% 8 == 0 and ldx %% 8 == 0 (N=%d ldx=%lld)", N, (long long)ldx);
+  return clipa::colsum_launch(x, ldx, out, rows, N, static_cast<cudaStream_t>(stream));
+}
+
+int clipa::colsum_launch(const void* x, long long ldx, float* out, long long rows, int N, cudaStream_t stream) {
   const int col_blocks = (N + 255) / 256;
   long long row_blocks = ((long long)num_sms() * 8 + col_blocks - 1) / col_blocks;
   long long rpb = (rows + row_blocks - 1) / row_blocks;
@@ -440,8 +481,7 @@ extern "C" int clipa_colsum_accum(const void* x, int64_t ldx, float* out, int64_
   rpb = (rpb + 7) / 8 * 8;
   row_blocks = (rows + rpb - 1) / rpb;
   dim3 grid(col_blocks, (unsigned)row_blocks);
-  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, out, rows, N, rpb);
+  colsum_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, out, rows, N, rpb);
   CLIPA_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CLIPA_OK;

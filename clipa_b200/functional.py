@@ -84,6 +84,14 @@ def _bgrad(dy: torch.Tensor, like: torch.Tensor) -> Optional[torch.Tensor]:
     return db if like.dtype == torch.float32 else db.to(like.dtype)
 
 
+def _bias_buf(bias: torch.Tensor):
+    """(fp32 accumulation target, direct): the parameter's flat .grad buffer when it opted in, else fresh zeros."""
+    sink = grad_sink(bias)
+    if sink is not None:
+        return sink, True
+    return torch.zeros(bias.shape, dtype=torch.float32, device=bias.device), False
+
+
 def _ln_grad_bufs(weight: torch.Tensor, bias: torch.Tensor):
     """(dgamma, dbeta, direct): accumulation targets for layernorm_bwd."""
     sg, sb = grad_sink(weight), grad_sink(bias)
@@ -156,7 +164,7 @@ class ResidualBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ln1_w, ln1_b, w_in, b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj,
-                b_proj, batch, seq, heads, causal, act, save_ln):
+                b_proj, batch, seq, heads, causal, act, save_ln, b_proj_prev=None, skip_b_proj=False):
         M, D = x.shape
         dev = x.device
         h1, mean1, rstd1 = ops.layernorm_fwd(x, _f32(ln1_w), _f32(ln1_b))
@@ -178,6 +186,12 @@ class ResidualBlockFn(torch.autograd.Function):
         ctx.save_for_backward(x, qkv, o, lse, x1, mean1, rstd1, mean2, rstd2, ln1_w, ln1_b, w_in,
                               b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj, h1, h2)
         ctx.meta = (batch, seq, heads, causal, act)
+        # Bias gradients that are column sums of a LayerNorm-backward OUTPUT are produced by that kernel:
+        # d(out_proj.bias) = colsum(dx1) here; d(c_proj.bias) of the PREVIOUS block = colsum(dx), the gradient this
+        # block hands down -- the previous block's bias rides along as an extra input (`b_proj_prev`) and that
+        # block skips its own column-sum pass (`skip_b_proj`).
+        ctx.prev_bias = b_proj_prev
+        ctx.skip_b_proj = skip_b_proj
         return y
 
     @staticmethod
@@ -185,6 +199,7 @@ class ResidualBlockFn(torch.autograd.Function):
         (x, qkv, o, lse, x1, mean1, rstd1, mean2, rstd2, ln1_w, ln1_b, w_in, b_in, w_out, b_out,
          ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj, h1, h2) = ctx.saved_tensors
         batch, seq, heads, causal, act = ctx.meta
+        b_prev = ctx.prev_bias
         M, D = x.shape
         dev = x.device
         dy = dy.contiguous()
@@ -196,7 +211,7 @@ class ResidualBlockFn(torch.autograd.Function):
         g = torch.empty(M, H4, dtype=_BF16, device=dev)
         ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), aux=f, act=act)
         d_w_proj = _wgrad(dy, g, w_proj)
-        d_b_proj = _bgrad(dy, b_proj)
+        d_b_proj = None if ctx.skip_b_proj else _bgrad(dy, b_proj)     # else: the next block's LayerNorm backward did it
         del g
         df = torch.empty(M, H4, dtype=_BF16, device=dev)
         ops.gemm(dy, compute_copy(w_proj).t(), df, epilogue=EPI_DACT, aux=f, act=act)
@@ -208,11 +223,12 @@ class ResidualBlockFn(torch.autograd.Function):
         ops.gemm(df, compute_copy(w_fc).t(), dh2)
         del df
         d_ln2_w, d_ln2_b, direct2 = _ln_grad_bufs(ln2_w, ln2_b)
-        dx1 = ops.layernorm_bwd(dh2, x1, _f32(ln2_w), mean2, rstd2, dy, d_ln2_w, d_ln2_b)
+        db_out, out_direct = _bias_buf(b_out)
+        dx1 = ops.layernorm_bwd(dh2, x1, _f32(ln2_w), mean2, rstd2, dy, d_ln2_w, d_ln2_b, dxsum=db_out)
+        d_b_out = None if out_direct else db_out.to(b_out.dtype)
         del dh2
         # ---- attention
         d_w_out = _wgrad(dx1, o, w_out)
-        d_b_out = _bgrad(dx1, b_out)
         do = torch.empty(M, D, dtype=_BF16, device=dev)
         ops.gemm(dx1, compute_copy(w_out).t(), do)
         dqkv = ops.attention_bwd(qkv, o, do, lse, batch, seq, heads, causal)
@@ -226,12 +242,16 @@ class ResidualBlockFn(torch.autograd.Function):
         ops.gemm(dqkv, compute_copy(w_in).t(), dh1)
         del dqkv
         d_ln1_w, d_ln1_b, direct1 = _ln_grad_bufs(ln1_w, ln1_b)
-        dx = ops.layernorm_bwd(dh1, x, _f32(ln1_w), mean1, rstd1, dx1, d_ln1_w, d_ln1_b)
+        db_prev = prev_direct = None
+        if b_prev is not None and ctx.needs_input_grad[19]:
+            db_prev, prev_direct = _bias_buf(b_prev)
+        dx = ops.layernorm_bwd(dh1, x, _f32(ln1_w), mean1, rstd1, dx1, d_ln1_w, d_ln1_b, dxsum=db_prev)
+        d_b_prev = None if (db_prev is None or prev_direct) else db_prev.to(b_prev.dtype)
         g_ln1 = (None, None) if direct1 else (d_ln1_w.to(ln1_w.dtype), d_ln1_b.to(ln1_b.dtype))
         g_ln2 = (None, None) if direct2 else (d_ln2_w.to(ln2_w.dtype), d_ln2_b.to(ln2_b.dtype))
         return (dx, g_ln1[0], g_ln1[1], d_w_in, d_b_in, d_w_out, d_b_out,
                 g_ln2[0], g_ln2[1], d_w_fc, d_b_fc, d_w_proj, d_b_proj,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, d_b_prev, None)
 
 
 class ClipLossFn(torch.autograd.Function):

@@ -92,13 +92,16 @@ class ResidualAttentionBlock(nn.Module):
         self.n_head = n_head
         self.act = ACT_BY_NAME[act]
 
-    def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool, save_ln: bool = False):
-        """x: [batch*seq, d_model] bf16, sample-major rows."""
+    def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool, save_ln: bool = False,
+                prev_proj_bias: Optional[torch.Tensor] = None, proj_bias_grad_by_next: bool = False):
+        """x: [batch*seq, d_model] bf16, sample-major rows.  prev_proj_bias / proj_bias_grad_by_next: the c_proj bias
+        gradient of a block is the column sum of the gradient the NEXT block's LayerNorm backward writes, so the next
+        block produces it (see functional.ResidualBlockFn)."""
         return Fn.ResidualBlockFn.apply(
             x, self.ln_1.weight, self.ln_1.bias, self.attn.in_proj_weight, self.attn.in_proj_bias,
             self.attn.out_proj.weight, self.attn.out_proj.bias, self.ln_2.weight, self.ln_2.bias,
             self.mlp.c_fc.weight, self.mlp.c_fc.bias, self.mlp.c_proj.weight, self.mlp.c_proj.bias,
-            batch, seq, self.n_head, causal, self.act, save_ln)
+            batch, seq, self.n_head, causal, self.act, save_ln, prev_proj_bias, proj_bias_grad_by_next)
 
 
 class _GradReady:
@@ -152,10 +155,12 @@ class Transformer(nn.Module):
     def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool = False):
         save_ln = self._decide_save_ln(x)
         cb = self.grad_ready_callback if torch.is_grad_enabled() else None
+        n_blocks = len(self.resblocks)
         for i, r in enumerate(self.resblocks):
             if cb is not None and x.requires_grad and i % self.grad_bucket_blocks == 0:
                 x.register_hook(_GradReady(cb, self, i))
-            x = r(x, batch, seq, causal, save_ln)
+            prev = self.resblocks[i - 1].mlp.c_proj.bias if i > 0 else None
+            x = r(x, batch, seq, causal, save_ln, prev, i + 1 < n_blocks)
         return x
 
 

@@ -151,15 +151,16 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres, dgamma, dbeta):
-    """Returns dx = dres + LN'(dy); accumulates into dgamma/dbeta (fp32)."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres, dgamma, dbeta, dxsum=None):
+    """Returns dx = dres + LN'(dy); accumulates into dgamma/dbeta (fp32) and, if given, the column sums of dx
+    into dxsum (fp32 [D]: a fused bias gradient)."""
     D = x.shape[-1]
     rows = x.numel() // D
     assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
     dx = torch.empty_like(x)
     with _prof(("ln_bwd", D), 0.0, (8.0 if dres is not None else 6.0) * rows * D):
         check(_lib.lib().clipa_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd),
-                                             _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), rows, D,
+                                             _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), rows, D,
                                              _stream()), "clipa_layernorm_bwd")
     return dx
 

@@ -97,10 +97,12 @@ int clipa_set_gemm_mode(int mode);
  * mean/rstd f32 [rows] are saved for backward (may be NULL in fwd). */
 int clipa_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,
                         float* rstd, int64_t rows, int32_t D, float eps, void* stream);
-/* dx = (dres ? dres : 0) + LN'(dy); dgamma/dbeta (f32 [D]) are ACCUMULATED (+=). */
+/* dx = (dres ? dres : 0) + LN'(dy); dgamma/dbeta (f32 [D]) are ACCUMULATED (+=).  dxsum (f32 [D], may be NULL):
+ * also += the column sums of the output dx -- the bias gradient of the Linear layer that fed the residual
+ * stream there (attn.out_proj / mlp.c_proj, open_clip/transformer.py:246-249), fused into this pass. */
 int clipa_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
                         const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
-                        int64_t rows, int32_t D, void* stream);
+                        float* dxsum, int64_t rows, int32_t D, void* stream);
 
 /* ---- multi-head self-attention core ---------------------------------------------------------
  * The SDPA inside nn.MultiheadAttention(need_weights=False) (open_clip/transformer.py:234-236):

@@ -126,9 +126,14 @@ def test_layernorm(dev, rows, D):
     dy, dres = mk((rows, D), dev), mk((rows, D), dev)
     yr.backward(dy.float())
     dg, db = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
-    dx = o.layernorm_bwd(dy, x, g, mean, rstd, dres, dg, db)
+    dxs = torch.full((D,), 0.25, device=dev)
+    dx = o.layernorm_bwd(dy, x, g, mean, rstd, dres, dg, db, dxsum=dxs)
     assert relmax(dx, xr.grad + dres.float()) < BF16_OUT
     assert relmax(dg, gr.grad) < 1e-3 and relmax(db, br.grad) < 1e-3
+    # fused column sums of the output (a bias gradient): accumulated (+=) onto the buffer, unrounded dx
+    assert relmax(dxs, 0.25 + (xr.grad + dres.float()).sum(0)) < 2e-3
+    dx2 = o.layernorm_bwd(dy, x, g, mean, rstd, dres, torch.zeros_like(dg), torch.zeros_like(db))
+    assert torch.equal(dx2, dx)
 
 
 def test_layernorm_constant_rows(dev):
