@@ -22,6 +22,9 @@ from ..ops import ACT_BY_NAME
 from .pos_embed import get_2d_sincos_pos_embed
 
 
+SUPPORTED_HEAD_DIMS = (64, 80, 96, 128)      # csrc/attention*.cu
+
+
 def to_2tuple(x):
     return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
 
@@ -80,6 +83,11 @@ class ResidualAttentionBlock(nn.Module):
         super().__init__()
         if ls_init_value is not None or is_cross_attention:
             raise NotImplementedError("LayerScale / cross-attention blocks are outside the CLIPA hot path")
+        if d_model % n_head or d_model // n_head not in SUPPORTED_HEAD_DIMS:
+            raise NotImplementedError(
+                f"head_dim {d_model / n_head:g} (width {d_model}, {n_head} heads): attention kernels exist for head_dim 64 "
+                "and 80 (tcgen05, any sequence length) and 96 / 128 (mma.sync, sequences up to ~380 tokens); "
+                "ViT-g/14 (88) and ViT-bigG/14 (104) are not built")
         self.ln_1 = LayerNorm(d_model)
         self.attn = nn.MultiheadAttention(d_model, n_head)   # parameter container only
         self.ln_2 = LayerNorm(d_model)

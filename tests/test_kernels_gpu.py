@@ -439,4 +439,4 @@ def test_clip_loss_column_chunking_matches_unchunked(dev, monkeypatch):
     (l0, g0), (l1, g1) = res
     assert abs(l0 - l1) < 1e-6
     for x, y in zip(g0, g1):
-        assert relmax(y, x) < 2e-3        # fp32 accumulation order differs between the two paths
+        assert relmax(y, x) < 1e-2        # outputs are bf16-rounded (1 ulp = 3.9e-3); fp32 accumulation order differs

@@ -43,7 +43,8 @@ def main():
     bl = B // world
     # --- N-rank step (micro-batch smaller than the local batch -> also exercises the GradCache path)
     for mb in (bl, bl // 2):
-        ts = TrainStep(model, rank=rank, world_size=world, micro_batch=mb)
+        # single-pass logit_scale gradient on both sides (the reference's accumulation loop counts it once per chunk)
+        ts = TrainStep(model, rank=rank, world_size=world, micro_batch=mb, reference_accum_logit_scale=False)
         ts.zero_grad()
         loss = ts.forward_backward(ts.preprocess(images[rank * bl:(rank + 1) * bl]), text[rank * bl:(rank + 1) * bl].to(dev))
         ts._allreduce_grads()
