@@ -8,9 +8,10 @@ Precision flags (training/precision.py:6-15, open_clip/model.py:78-86):
   'amp_bf16'           fp32 master weights; the kernels read bf16 shadow copies refreshed after every
                        optimizer step, gradients are fp32 (the reference's autocast runs the same
                        matmuls in bf16).
-  'fp32' / 'amp' / 'fp16'  NOT computed: no fp32 (or fp16) arithmetic exists on this path.  The model can
-                       be built (state_dict schema, checkpoint conversion) but forward() raises instead of
-                       silently substituting bf16 math.
+  'fp32'               fp32 weights, activations and arithmetic on CUDA-core kernels (clipa_b200/fp32_path.py):
+                       the reference-exact parity mode (1e-5), orders of magnitude slower than the tensor-core path.
+  'amp' / 'fp16'       NOT computed (no fp16 arithmetic): the model can be built (state_dict schema, checkpoint
+                       conversion) but forward() raises instead of silently substituting other math.
 """
 from __future__ import annotations
 
@@ -77,8 +78,8 @@ def create_model(model_name: str, pretrained: Optional[str] = None, precision: s
     custom_text = model_cfg.pop('custom_text', False) or force_custom_text          # factory.py:203-211
     cast_dtype = get_cast_dtype(precision)
     model = (CustomTextCLIP if custom_text else CLIP)(**model_cfg, cast_dtype=cast_dtype)
-    # 'fp32' (the reference's default) / 'amp' / 'fp16' models can be built, saved and loaded, but refuse to run:
-    # there is no fp32 or fp16 arithmetic in this library (model.check_compute_precision)
+    # 'amp' / 'fp16' models can be built, saved and loaded, but refuse to run (model.check_compute_precision);
+    # 'fp32' runs the CUDA-core parity path
     model.compute_precision = precision
     if precision not in COMPUTE_PRECISIONS:
         logging.warning("precision=%r: built as a parameter container only; forward() needs 'amp_bf16' or 'bf16'",

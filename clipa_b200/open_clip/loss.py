@@ -19,6 +19,7 @@ except ImportError:  # pragma: no cover
     dist = None
     has_distributed = False
 
+from .. import fp32_path
 from .. import functional as Fn
 
 
@@ -77,21 +78,25 @@ class ClipLoss(nn.Module):
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         if not image_features.is_cuda:
             raise RuntimeError("clipa_b200.ClipLoss runs on CUDA tensors only (no CPU fallback)")
-        image_features = image_features.to(torch.bfloat16)
-        text_features = text_features.to(torch.bfloat16)
+        if image_features.dtype == torch.float32 and text_features.dtype == torch.float32:
+            loss_fn = fp32_path.ClipLossF32        # features of a precision='fp32' model: fp32 head (parity mode)
+        else:
+            loss_fn = Fn.ClipLossFn
+            image_features = image_features.to(torch.bfloat16)
+            text_features = text_features.to(torch.bfloat16)
         if self.world_size > 1:
             all_image, all_text = gather_features(
                 image_features, text_features, self.local_loss, self.gather_with_grad, self.rank,
                 self.world_size, self.use_horovod)
             if self.local_loss:
                 # without gather_with_grad the gathered tensors are constants here: skip their gradient GEMMs
-                total_loss = Fn.ClipLossFn.apply(image_features, text_features, all_image, all_text,
+                total_loss = loss_fn.apply(image_features, text_features, all_image, all_text,
                                                  logit_scale, self.rank, self.gather_with_grad)
             else:
                 # full-matrix form (loss.py:138-139): every rank evaluates all rows
-                total_loss = Fn.ClipLossFn.apply(all_image, all_text, all_image, all_text,
+                total_loss = loss_fn.apply(all_image, all_text, all_image, all_text,
                                                  logit_scale, 0, True)
         else:
-            total_loss = Fn.ClipLossFn.apply(image_features, text_features, image_features,
+            total_loss = loss_fn.apply(image_features, text_features, image_features,
                                              text_features, logit_scale, 0, True)
         return {"contrastive_loss": total_loss} if output_dict else total_loss

@@ -13,6 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .. import fp32_path
 from .. import functional as Fn
 from .transformer import text_tower_forward  # noqa: E402
 from .transformer import LayerNorm, TextTransformer, VisionTransformer
@@ -157,12 +158,16 @@ class CLIP(nn.Module):
         self.transformer.grad_checkpointing = enable
 
     def encode_image(self, image, normalize: bool = False):
-        check_compute_precision(self)
+        if check_compute_precision(self) == 'fp32':
+            features = fp32_path.encode_image(self.visual, image)
+            return F.normalize(features, dim=-1) if normalize else features
         features = self.visual(image)
         return _l2_normalize(features) if normalize else features
 
     def encode_text(self, text, normalize: bool = False):
-        check_compute_precision(self)
+        if check_compute_precision(self) == 'fp32':
+            x = fp32_path.encode_text(self, text, slice_positions=False)
+            return F.normalize(x, dim=-1) if normalize else x
         x = text_tower_forward(self, text, slice_positions=False)
         return _l2_normalize(x) if normalize else x
 
@@ -202,12 +207,16 @@ class CustomTextCLIP(nn.Module):
         self.text.set_grad_checkpointing(enable)
 
     def encode_image(self, image, normalize: bool = False):
-        check_compute_precision(self)
+        if check_compute_precision(self) == 'fp32':
+            features = fp32_path.encode_image(self.visual, image)
+            return F.normalize(features, dim=-1) if normalize else features
         features = self.visual(image)
         return _l2_normalize(features) if normalize else features
 
     def encode_text(self, text, normalize: bool = False):
-        check_compute_precision(self)
+        if check_compute_precision(self) == 'fp32':
+            features = fp32_path.encode_text(self.text, text, slice_positions=True)
+            return F.normalize(features, dim=-1) if normalize else features
         features = self.text(text)
         return _l2_normalize(features) if normalize else features
 
@@ -229,20 +238,21 @@ def convert_to_custom_text_state_dict(state_dict: dict):
 
 
 # Precision flags whose arithmetic this library implements (training/precision.py, open_clip/model.py:78-86):
-# fp32 master weights with bf16 tensor-core math ('amp_bf16'), or bf16 weights ('bf16').
-COMPUTE_PRECISIONS = ('amp_bf16', 'amp_bfloat16', 'bf16', 'pure_bf16')
+# fp32 master weights with bf16 tensor-core math ('amp_bf16'), bf16 weights ('bf16'), and 'fp32' = fp32 storage AND
+# arithmetic on CUDA-core kernels (clipa_b200/fp32_path.py: the 1e-5 parity mode, not a throughput path).
+COMPUTE_PRECISIONS = ('amp_bf16', 'amp_bfloat16', 'bf16', 'pure_bf16', 'fp32')
 
 
-def check_compute_precision(model) -> None:
-    """A model built with any other flag (the factory's default 'fp32', 'amp' = fp16 autocast, 'fp16') is only a
-    parameter container (state_dict / checkpoint conversion): running it would silently replace the requested
-    arithmetic by bf16 tensor-core math, so it refuses."""
+def check_compute_precision(model) -> str:
+    """Returns 'fp32' or 'bf16' (the arithmetic to run).  A model built with any other flag ('amp' = fp16 autocast,
+    'fp16') is only a parameter container (state_dict / checkpoint conversion): running it would silently replace the
+    requested arithmetic, so it refuses."""
     flag = getattr(model, 'compute_precision', 'amp_bf16')
     if flag not in COMPUTE_PRECISIONS:
         raise NotImplementedError(
-            f"precision={flag!r}: no fp32 / fp16 compute path is built -- the sm_100a kernels multiply in bf16 with "
-            "fp32 accumulation.  Build the model with precision='amp_bf16' (fp32 master weights, the mode of every "
-            "reference GPU script) or 'bf16'.")
+            f"precision={flag!r}: no fp16 compute path is built.  Build the model with precision='amp_bf16' (fp32 master "
+            "weights + bf16 tensor-core math, the mode of every reference GPU script), 'bf16', or 'fp32' (parity mode).")
+    return 'fp32' if flag == 'fp32' else 'bf16'
 
 
 def resize_pos_embed(state_dict, model, interpolation: str = 'bicubic', antialias: bool = True):

@@ -209,6 +209,36 @@ int clipa_l2_normalize(const void* x, void* y, int64_t ldy, float* inv_norm, int
 int clipa_l2_normalize_bwd(const void* x, const float* inv_norm, const void* dy, int32_t dy_dtype, void* dx,
                            int64_t rows, int32_t E, void* stream);
 
+/* ---- fp32 parity path (precision='fp32'; north_star "1e-5 (fp32)") ----------------------------------------
+ * The same call sites as above on CUDA-core kernels with fp32 storage and fp32 FMA arithmetic (tcgen05 has no
+ * fp32 MMA).  Parity only -- not a throughput path.  All pointers f32.
+ *   clipa_gemm_f32: C[m,n] (=|+=) alpha * sum_k A[m*rsa + k*csa] * B[n*rsb + k*csb] (+ bias[n]) (+ residual[m,n])
+ *                   (element strides: transposed operands are read in place)
+ *   clipa_act_f32:  out = act(x) or, with derivative != 0, dy * act'(x)               (clipa_act)
+ *   clipa_layernorm_f32_fwd/_bwd: F.layer_norm and its backward (dgamma / dbeta accumulated)
+ *   clipa_attention_f32_fwd/_bwd: same contract as clipa_attention_fwd/_bwd with f32 qkv / out / dqkv
+ *   clipa_colsum_f32: out[n] += sum_m x[m,n]
+ *   clipa_row_lse_f32: lse[m] = logsumexp_n logits[m,n], diag[m] = logits[m, m + label_offset]   (ClipLoss,
+ *                   open_clip/loss.py:152-155 over materialised logits)
+ *   clipa_softmax_grad_f32: pt = softmax(logits) - onehot; dscale += sum pt * logits / scale (scale in device memory) */
+int clipa_gemm_f32(int32_t M, int32_t N, int32_t K, const float* A, int64_t rsa, int64_t csa, const float* B,
+                   int64_t rsb, int64_t csb, float* C, int64_t ldc, float alpha, const float* bias,
+                   const float* residual, int64_t ldr, int32_t accumulate, void* stream);
+int clipa_act_f32(const float* x, const float* dy, float* out, int64_t n, int32_t act, int32_t derivative, void* stream);
+int clipa_layernorm_f32_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                            int64_t rows, int32_t D, float eps, void* stream);
+int clipa_layernorm_f32_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                            float* dx, float* dgamma, float* dbeta, int64_t rows, int32_t D, void* stream);
+int clipa_attention_f32_fwd(const float* qkv, float* out, float* lse, int32_t batch, int32_t L, int32_t heads,
+                            int32_t head_dim, int32_t causal, void* stream);
+int clipa_attention_f32_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv,
+                            int32_t batch, int32_t L, int32_t heads, int32_t head_dim, int32_t causal, void* stream);
+int clipa_colsum_f32(const float* x, int64_t ldx, float* out, int64_t rows, int32_t N, void* stream);
+int clipa_row_lse_f32(const float* logits, int64_t ld, int32_t M, int32_t N, int32_t label_offset, float* lse,
+                      float* diag, void* stream);
+int clipa_softmax_grad_f32(const float* logits, int64_t ld, int32_t M, int32_t N, int32_t label_offset,
+                           const float* lse, const float* scale_dev, float* pt, float* dscale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

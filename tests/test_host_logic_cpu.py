@@ -297,22 +297,24 @@ def test_grad_sink_is_opt_in():
 
 
 def test_unbuilt_precisions_refuse_to_run():
-    """precision='fp32' (the factory default), 'amp' and 'fp16' have no arithmetic on this path: the model is a
-    parameter container (schema / checkpoints) and forward() raises instead of silently running bf16 math."""
+    """precision='amp' (fp16 autocast) and 'fp16' have no arithmetic on this path: the model is a parameter container
+    (schema / checkpoints) and forward() raises instead of silently running other math.  'fp32' (the factory default)
+    is the CUDA-core parity mode: it passes the precision check and then, like every mode, refuses CPU tensors."""
     import torch
     from clipa_b200 import open_clip
-    m = open_clip.create_model("ViT-B-32-CL16", precision="fp32", device="cpu", force_image_size=64)
-    assert m.compute_precision == "fp32" and next(m.parameters()).dtype == torch.float32
+    m = open_clip.create_model("ViT-B-32-CL16", precision="amp", device="cpu", force_image_size=64)
+    assert m.compute_precision == "amp" and next(m.parameters()).dtype == torch.float32
     with pytest.raises(NotImplementedError, match="amp_bf16"):
         m(torch.zeros(1, 3, 64, 64), torch.zeros(1, 16, dtype=torch.long))
     with pytest.raises(NotImplementedError, match="amp_bf16"):
         m.encode_text(torch.zeros(1, 16, dtype=torch.long))
     with pytest.raises(NotImplementedError):
         open_clip.create_model("ViT-B-32-CL16", precision="fp16", device="cpu")
-    ok = open_clip.create_model("ViT-B-32-CL16", precision="amp_bf16", device="cpu", force_image_size=64)
-    with pytest.raises(Exception) as e:     # the precision check passes; the kernels then refuse CPU tensors
-        ok.encode_text(torch.zeros(1, 16, dtype=torch.long))
-    assert not isinstance(e.value, NotImplementedError)
+    for prec in ("amp_bf16", "fp32"):
+        ok = open_clip.create_model("ViT-B-32-CL16", precision=prec, device="cpu", force_image_size=64)
+        with pytest.raises(Exception) as e:     # the precision check passes; the kernels then refuse CPU tensors
+            ok.encode_text(torch.zeros(1, 16, dtype=torch.long))
+        assert not isinstance(e.value, NotImplementedError)
 
 
 def test_custom_text_clip_schema_and_checkpoint_conversion():

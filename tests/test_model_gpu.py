@@ -366,9 +366,54 @@ def test_custom_text_clip_matches_clip(dev):
             clip.encode_text(short)
 
 
-def test_fp32_precision_refuses_to_run_on_gpu(dev):
+FP32_CASES = CASES + ["vitl14-i81-t16-d2", "vith14-i36-t8-d2", "vitb16-i64-t16-d3", "vitl14-i256-t32-d2"]
+
+
+@pytest.mark.parametrize("name", FP32_CASES)
+def test_fp32_mode_matches_reference_fp32(dev, name):
+    """north_star "within 1e-5 (fp32)": precision='fp32' (CUDA-core fp32 kernels, clipa_b200/fp32_path.py) against the
+    reference's fp32 run -- features and loss to 1e-5 relative, gradients to 5e-5 -- on the small cases and at the
+    BASELINE widths / head shapes / sequence lengths (batch 32)."""
+    meta, g = load_golden(name, "fp32")
+    model, text, out, loss = run_ours(meta, "fp32", dev)
+    assert out["image_features"].dtype == torch.float32 and loss.dtype == torch.float32
+    params = dict(model.named_parameters())
+    compact = meta.get("compact", False)
+    cut = (lambda t: t[:64, :64]) if compact else (lambda t: t)
+    last = meta["cfg"]["vision_cfg"]["layers"] - 1
+    rows = torch.as_tensor(g["token_rows_idx"])
+    rec = {"case": name, "precision": "fp32", "errors": {}}
+    checks = {
+        "image_features": (out["image_features"].detach(), 1e-5), "text_features": (out["text_features"].detach(), 1e-5),
+        "d_image_features": (out["image_features"].grad, 5e-5), "d_text_features": (out["text_features"].grad, 5e-5),
+        "g_visual_proj": (cut(params["visual.proj"].grad), 5e-5),
+        "g_text_projection": (cut(params["text_projection"].grad), 5e-5),
+        "g_v0_in_proj_weight": (params["visual.transformer.resblocks.0.attn.in_proj_weight"].grad[:64, :64], 1e-4),
+        "g_v0_in_proj_bias": (params["visual.transformer.resblocks.0.attn.in_proj_bias"].grad, 1e-4),
+        "g_vlast_c_fc_bias": (params[f"visual.transformer.resblocks.{last}.mlp.c_fc.bias"].grad, 1e-4),
+        "g_t0_ln_1_weight": (params["transformer.resblocks.0.ln_1.weight"].grad, 1e-4),
+        "g_class_embedding": (params["visual.class_embedding"].grad, 1e-4),
+        "g_token_rows": (params["token_embedding.weight"].grad[rows.to(dev)], 1e-4),
+    }
+    bad = []
+    for k, (v, tol) in checks.items():
+        e = rel_err(v.float().cpu(), g[k])
+        rec["errors"][k] = e
+        if not e < tol:
+            bad.append((k, e, tol))
+    l32 = float(g["loss"])
+    rec["loss"] = {"ours": loss.item(), "ref_fp32": l32, "rel_err": abs(loss.item() - l32) / l32}
+    gs = params["logit_scale"].grad.item()
+    rec["g_logit_scale"] = {"ours": gs, "ref_fp32": float(g["g_logit_scale"])}
+    _report(rec)
+    assert rec["loss"]["rel_err"] < 1e-5, rec["loss"]
+    assert abs(gs - float(g["g_logit_scale"])) <= 1e-4 * abs(float(g["g_logit_scale"])) + 1e-7, rec["g_logit_scale"]
+    assert not bad, bad
+
+
+def test_fp16_precision_refuses_to_run_on_gpu(dev):
     from clipa_b200 import open_clip
-    m = open_clip.create_model("ViT-B-32-CL16", precision="fp32", device=dev, force_image_size=64)
+    m = open_clip.create_model("ViT-B-32-CL16", precision="amp", device=dev, force_image_size=64)
     with pytest.raises(NotImplementedError, match="amp_bf16"):
         m(torch.zeros(2, 3, 64, 64, device=dev), torch.zeros(2, 16, dtype=torch.long, device=dev))
 
