@@ -31,6 +31,10 @@ for rows, D in [(82 * 4096, 1024), (16 * 4096, 768), (37 * 2048, 1280)]:
     tf = timeit(lambda: ops.layernorm_fwd(x, g, b))
     tb = timeit(lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, dres, dg, db))
     tb2 = timeit(lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, None, dg, db))
+    dxs = torch.zeros(D, device=dev)
+    tb3 = timeit(lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, dres, dg, db, dxsum=dxs))
+    tc = timeit(lambda: ops.colsum_accum(dy, dxs))
     n = rows * D
     print(f"PERF ln rows={rows} D={D}: fwd {tf:.1f} us ({4 * n / tf / 1e3:.0f} GB/s)  "
-          f"bwd+dres {tb:.1f} us ({8 * n / tb / 1e3:.0f} GB/s)  bwd {tb2:.1f} us ({6 * n / tb2 / 1e3:.0f} GB/s)")
+          f"bwd+dres {tb:.1f} us ({8 * n / tb / 1e3:.0f} GB/s)  bwd {tb2:.1f} us ({6 * n / tb2 / 1e3:.0f} GB/s)  "
+          f"bwd+dres+dxsum {tb3:.1f} us ({8 * n / tb3 / 1e3:.0f} GB/s; separate column-sum pass: {tc:.1f} us)")
