@@ -164,7 +164,7 @@ def cpu_baseline(wl, budget_s=20.0, batch=8):
                       f"batch {batch}, {n} steps after 1 warm-up, fp32, torch CPU threads={cores}"}
 
 
-def library_baseline_leg(wl, batch, trainer, model):
+def library_baseline_leg(wl, batch):
     """Bounded sample of the "library Blackwell path to beat" (SURVEY 8d): the unmodified reference
     (baseline/_ref) on torch's CUDA kernels, same box, right after our timed region.  Reported beside the
     headline, never part of it."""
@@ -173,9 +173,9 @@ def library_baseline_leg(wl, batch, trainer, model):
     from baseline.ref_loader import available
     if not available():
         return {"unavailable": "baseline/_ref not installed (tools/install_reference.sh)"}
-    del trainer, model
     gc.collect()
     torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
     try:
         from baseline.library_step import library_baseline
         r = library_baseline(wl, batch, steps=3, warmup=2)
@@ -388,7 +388,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(wl, batch=args.cpu_batch)
         if world == 1 and not args.no_library_baseline:
-            out["library_baseline"] = library_baseline_leg(wl, args.library_batch, trainer, model)
+            # release OUR model, optimizer state and activations first: the comparison arm gets the whole GPU
+            trainer.model = None
+            del trainer, model, d_images, d_text
+            out["library_baseline"] = library_baseline_leg(wl, args.library_batch)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -84,6 +84,23 @@ def _bgrad(dy: torch.Tensor, like: torch.Tensor) -> Optional[torch.Tensor]:
     return db if like.dtype == torch.float32 else db.to(like.dtype)
 
 
+def _in_proj_bias_grad(dqkv: torch.Tensor, b_in: torch.Tensor, db_out: torch.Tensor, w_out: torch.Tensor, D: int):
+    """d(in_proj_bias) = column sums of dqkv = [sum dQ | sum dK | sum dV], with two thirds of the pass removed:
+      * sum_j dK_j = sum_i (sum_j dS_ij) Q_i = 0 exactly: rows of dS = P o (dP - delta) sum to delta - delta (a constant
+        added to every key of a sample does not change its softmax), so the K part is left untouched;
+      * sum_j dV_j = sum_i (sum_j P_ij) dO_i = sum_i dO_i, and dO = dx1 @ W_out, so the V part is the tiny product
+        d(out_proj.bias) @ W_out (fp32, CUDA-core kernel) of a vector LayerNorm-backward has already produced;
+      * only the Q third needs a pass over dqkv."""
+    from . import fp32_path
+    sink = grad_sink(b_in)
+    buf = sink if sink is not None else torch.zeros(3 * D, dtype=torch.float32, device=dqkv.device)
+    ops.colsum_accum(dqkv[:, :D], buf[:D])
+    fp32_path.gemm_f32(db_out.view(1, D), _f32(w_out).t(), buf[2 * D:].view(1, D), accumulate=True)
+    if sink is not None:
+        return None
+    return buf if b_in.dtype == torch.float32 else buf.to(b_in.dtype)
+
+
 def _bias_buf(bias: torch.Tensor):
     """(fp32 accumulation target, direct): the parameter's flat .grad buffer when it opted in, else fresh zeros."""
     sink = grad_sink(bias)
@@ -223,9 +240,15 @@ class ResidualBlockFn(torch.autograd.Function):
         ops.gemm(df, compute_copy(w_fc).t(), dh2)
         del df
         d_ln2_w, d_ln2_b, direct2 = _ln_grad_bufs(ln2_w, ln2_b)
-        db_out, out_direct = _bias_buf(b_out)
+        # fresh buffer (not the accumulating .grad sink): this step's value also yields the V-bias gradient below
+        db_out = torch.zeros(D, dtype=torch.float32, device=dev)
         dx1 = ops.layernorm_bwd(dh2, x1, _f32(ln2_w), mean2, rstd2, dy, d_ln2_w, d_ln2_b, dxsum=db_out)
-        d_b_out = None if out_direct else db_out.to(b_out.dtype)
+        sink_out = grad_sink(b_out)
+        if sink_out is not None:
+            sink_out.add_(db_out)
+            d_b_out = None
+        else:
+            d_b_out = db_out.to(b_out.dtype)
         del dh2
         # ---- attention
         d_w_out = _wgrad(dx1, o, w_out)
@@ -236,7 +259,7 @@ class ResidualBlockFn(torch.autograd.Function):
         if h1 is None:
             h1, _, _ = ops.layernorm_fwd(x, _f32(ln1_w), _f32(ln1_b), save_stats=False)
         d_w_in = _wgrad(dqkv, h1, w_in)
-        d_b_in = _bgrad(dqkv, b_in)
+        d_b_in = _in_proj_bias_grad(dqkv, b_in, db_out, w_out, D)
         del h1
         dh1 = torch.empty(M, D, dtype=_BF16, device=dev)
         ops.gemm(dqkv, compute_copy(w_in).t(), dh1)
