@@ -368,6 +368,7 @@ def main():
                        "loss_last": float(last_loss),
                        "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
                        "save_ln_outputs": str(type(model.visual.transformer).save_ln_outputs),
+
                        "algorithmic_gflop_per_pair": wl["gflop_per_pair"],
                        "model_flops_utilization": per_gpu_pairs * wl["gflop_per_pair"] / (peak * 1e3)},
             "clocks": clocks, "gpu_launches": launches,

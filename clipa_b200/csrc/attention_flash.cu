@@ -860,6 +860,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
       mbar_wait(sdp_full, k & 1);
       tc_fence_after();
       const float lse2 = lse_raw * 1.4426950408889634f;
+      const float nds = -delta * p.scale;
       if (k + 1 < K) {                       // next step's lse: consumed one whole stage later
         lse_raw = lse_of(cl);
         if (cl.advance() && cl.it < n_local) decode(cl);
@@ -873,13 +874,10 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
           tmem_ld_32x16(t_row + kColDp + c, dv);
           tmem_ld_wait();
           float pr[16], ds[16];
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const bool ok = row_ok && (c + jj) < hi && (c + jj) >= lo;
-            const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[jj]), scale_log2, -lse2)) : 0.f;
-            pr[jj] = pv;
-            ds[jj] = pv * (__uint_as_float(dv[jj]) - delta) * p.scale;
-          }
+          if (row_ok && c >= lo && c + 16 <= hi)
+            attn_bwd_chunk16<false>(sv, dv, scale_log2, lse2, p.scale, nds, c, lo, hi, row_ok, pr, ds);
+          else
+            attn_bwd_chunk16<true>(sv, dv, scale_log2, lse2, p.scale, nds, c, lo, hi, row_ok, pr, ds);
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
             const uint32_t off = fb_tile_off(row, (c >> 3) + g8);

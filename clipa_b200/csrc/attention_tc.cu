@@ -613,6 +613,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       mbar_wait(sdp_full, pi);
       tc_fence_after();
       const float lse2 = lse_raw * 1.4426950408889634f;
+      const float nds = -delta * p.scale;
+      const int mlo = PACKED ? span.lo : 0;
       if (i + 1 < n_local && row_in_tile) {
         const long long li = lse_index(prob + (int)gridDim.x);
         lse_raw = li >= 0 ? p.lse[li] : 0.f;
@@ -624,14 +626,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
           tmem_ld_32x16(t_row + kColDp + c, dv);
           tmem_ld_wait();
           float pr[16], ds[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int key = c + j;
-            const bool ok = row_ok && (!PACKED || key >= span.lo) && key < span.hi;
-            const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[j]), scale_log2, -lse2)) : 0.f;
-            pr[j] = pv;
-            ds[j] = pv * (__uint_as_float(dv[j]) - delta) * p.scale;
-          }
+          if (row_ok && c >= mlo && c + 16 <= span.hi)
+            attn_bwd_chunk16<false>(sv, dv, scale_log2, lse2, p.scale, nds, c, mlo, span.hi, row_ok, pr, ds);
+          else
+            attn_bwd_chunk16<true>(sv, dv, scale_log2, lse2, p.scale, nds, c, mlo, span.hi, row_ok, pr, ds);
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
             const uint32_t off = p_tile_off(row, (c >> 3) + g8);
@@ -859,6 +857,7 @@ attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       mbar_wait(sdp_full, j & 1);
       tc_fence_after();
       const float lse2 = lse_raw * 1.4426950408889634f;
+      const float nds = -delta * p.scale;
       if (j + 1 < n_local && row_ok)   // next problem's lse: consumed one whole stage later
         lse_raw = p.lse[(long long)(prob + (int)gridDim.x) * L + row];
       if (warp_writes) {
@@ -870,13 +869,10 @@ attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           tmem_ld_32x16(t_row + kColDp + c, dv);
           tmem_ld_wait();
           float pr[16], ds[16];
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const bool ok = row_ok && (c + jj) < hi;
-            const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[jj]), scale_log2, -lse2)) : 0.f;
-            pr[jj] = pv;
-            ds[jj] = pv * (__uint_as_float(dv[jj]) - delta) * p.scale;
-          }
+          if (row_ok && c + 16 <= hi)
+            attn_bwd_chunk16<false>(sv, dv, scale_log2, lse2, p.scale, nds, c, 0, hi, row_ok, pr, ds);
+          else
+            attn_bwd_chunk16<true>(sv, dv, scale_log2, lse2, p.scale, nds, c, 0, hi, row_ok, pr, ds);
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
             const uint32_t off = p96_tile_off(row, (c >> 3) + g8);

@@ -27,4 +27,29 @@ __device__ __forceinline__ uint32_t p_tile_off(int row, int chunk) {
   return (chunk >> 3) * kTcTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
 }
 
+// Elementwise stage of the attention backward for 16 key columns of one query row:
+//   P = 2^(S*scale_log2 - lse2),   dS = P * (dP - delta) * scale = P * (dP*scale + nds),  nds = -delta*scale
+// on the packed-fp32 pipe (one FFMA2 for the exponent pair, one FFMA2 + one FMUL2 for the dS pair).  MASKED: columns
+// outside [lo, hi) (padding, other samples of a packed tile, causal future) and rows that do not exist give P = dS = 0;
+// chunks that lie inside the valid range take the predicate-free variant.
+template <bool MASKED>
+__device__ __forceinline__ void attn_bwd_chunk16(const uint32_t (&sv)[16], const uint32_t (&dv)[16], float scale_log2,
+                                                 float lse2, float scale, float nds, int c, int lo, int hi, bool row_ok,
+                                                 float (&pr)[16], float (&ds)[16]) {
+  const float2 sl2 = splat2(scale_log2), nl2 = splat2(-lse2), sc2 = splat2(scale), nd2 = splat2(nds);
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const float2 t = fma2(make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), sl2, nl2);
+    float p0 = ex2_approx(t.x), p1 = ex2_approx(t.y);
+    if (MASKED) {
+      p0 = (row_ok && c + j >= lo && c + j < hi) ? p0 : 0.f;
+      p1 = (row_ok && c + j + 1 >= lo && c + j + 1 < hi) ? p1 : 0.f;
+    }
+    const float2 d = fma2(make_float2(__uint_as_float(dv[j]), __uint_as_float(dv[j + 1])), sc2, nd2);
+    const float2 g = mul2(make_float2(p0, p1), d);
+    pr[j] = p0; pr[j + 1] = p1;
+    ds[j] = g.x; ds[j + 1] = g.y;
+  }
+}
+
 }  // namespace clipa

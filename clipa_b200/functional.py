@@ -181,7 +181,7 @@ class ResidualBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ln1_w, ln1_b, w_in, b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj,
-                b_proj, batch, seq, heads, causal, act, save_ln, b_proj_prev=None, skip_b_proj=False):
+                b_proj, batch, seq, heads, causal, act, save_ln, b_proj_prev=None, skip_b_proj=False, drop_o=False):
         M, D = x.shape
         dev = x.device
         h1, mean1, rstd1 = ops.layernorm_fwd(x, _f32(ln1_w), _f32(ln1_b))
@@ -200,6 +200,8 @@ class ResidualBlockFn(torch.autograd.Function):
         y = torch.empty(M, D, dtype=_BF16, device=dev)
         ops.gemm(g, compute_copy(w_proj), y, bias=_bias(b_proj), residual=x1)
         del g
+        if drop_o:
+            o = None        # recomputed from qkv in backward (Transformer._activation_policy: HBM is tight)
         ctx.save_for_backward(x, qkv, o, lse, x1, mean1, rstd1, mean2, rstd2, ln1_w, ln1_b, w_in,
                               b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj, h1, h2)
         ctx.meta = (batch, seq, heads, causal, act)
@@ -251,6 +253,8 @@ class ResidualBlockFn(torch.autograd.Function):
             d_b_out = db_out.to(b_out.dtype)
         del dh2
         # ---- attention
+        if o is None:
+            o, _ = ops.attention_fwd(qkv, batch, seq, heads, causal)
         d_w_out = _wgrad(dx1, o, w_out)
         do = torch.empty(M, D, dtype=_BF16, device=dev)
         ops.gemm(dx1, compute_copy(w_out).t(), do)
@@ -274,7 +278,7 @@ class ResidualBlockFn(torch.autograd.Function):
         g_ln2 = (None, None) if direct2 else (d_ln2_w.to(ln2_w.dtype), d_ln2_b.to(ln2_b.dtype))
         return (dx, g_ln1[0], g_ln1[1], d_w_in, d_b_in, d_w_out, d_b_out,
                 g_ln2[0], g_ln2[1], d_w_fc, d_b_fc, d_w_proj, d_b_proj,
-                None, None, None, None, None, None, d_b_prev, None)
+                None, None, None, None, None, None, d_b_prev, None, None)
 
 
 class ClipLossFn(torch.autograd.Function):

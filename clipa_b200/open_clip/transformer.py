@@ -101,7 +101,8 @@ class ResidualAttentionBlock(nn.Module):
         self.act = ACT_BY_NAME[act]
 
     def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool, save_ln: bool = False,
-                prev_proj_bias: Optional[torch.Tensor] = None, proj_bias_grad_by_next: bool = False):
+                prev_proj_bias: Optional[torch.Tensor] = None, proj_bias_grad_by_next: bool = False,
+                recompute_attn_out: bool = False):
         """x: [batch*seq, d_model] bf16, sample-major rows.  prev_proj_bias / proj_bias_grad_by_next: the c_proj bias
         gradient of a block is the column sum of the gradient the NEXT block's LayerNorm backward writes, so the next
         block produces it (see functional.ResidualBlockFn)."""
@@ -109,7 +110,8 @@ class ResidualAttentionBlock(nn.Module):
             x, self.ln_1.weight, self.ln_1.bias, self.attn.in_proj_weight, self.attn.in_proj_bias,
             self.attn.out_proj.weight, self.attn.out_proj.bias, self.ln_2.weight, self.ln_2.bias,
             self.mlp.c_fc.weight, self.mlp.c_fc.bias, self.mlp.c_proj.weight, self.mlp.c_proj.bias,
-            batch, seq, self.n_head, causal, self.act, save_ln, prev_proj_bias, proj_bias_grad_by_next)
+            batch, seq, self.n_head, causal, self.act, save_ln, prev_proj_bias, proj_bias_grad_by_next,
+            recompute_attn_out)
 
 
 class _GradReady:
@@ -140,20 +142,35 @@ class Transformer(nn.Module):
     def get_cast_dtype(self) -> torch.dtype:
         return self.resblocks[0].mlp.c_fc.weight.dtype
 
-    # 'auto': keep the LayerNorm outputs of every block for backward when they fit comfortably in
-    # free HBM (2 extra activation-sized tensors per block), else recompute them; True / False force it.
+    # Activation memory policy per tower, chosen from the free HBM at forward time ('auto'), one "unit" = one
+    # [batch*L, width] bf16 tensor:
+    #   8 units / block  x, qkv (3), o, x1 + the two LayerNorm outputs     when it fits with a 16 GB margin
+    #   6 units / block  LayerNorm outputs recomputed in backward          default
+    #   5 units / block  attention output o recomputed too (one extra attention forward per block, ~2 % of a step)
+    #                    when even 6 units + 8 GB would not fit (ViT-H/14 at 8192 pairs per GPU: 2 GiB were left)
+    # save_ln_outputs / recompute_attn_out = True / False force a level.
     save_ln_outputs = "auto"
+    recompute_attn_out = "auto"
 
-    def _decide_save_ln(self, x: torch.Tensor) -> bool:
+    def _activation_policy(self, x: torch.Tensor):
+        """-> (save_ln, drop_o)"""
         if not torch.is_grad_enabled() or not x.is_cuda:
-            return False
-        if self.save_ln_outputs != "auto":
-            return bool(self.save_ln_outputs)
+            return False, False
         unit = x.numel() * x.element_size()
-        need = (8 * self.layers + 16) * unit          # 8 saved tensors per block + backward temporaries
         free, _ = torch.cuda.mem_get_info(x.device)
         free += torch.cuda.memory_reserved(x.device) - torch.cuda.memory_allocated(x.device)
-        return need + (16 << 30) < free                # keep a 16 GB margin for the other tower / head
+        if self.save_ln_outputs == "auto":
+            save_ln = (8 * self.layers + 16) * unit + (16 << 30) < free   # 8 saved tensors per block + backward temporaries
+        else:
+            save_ln = bool(self.save_ln_outputs)
+        if self.recompute_attn_out == "auto":
+            drop_o = (not save_ln) and (6 * self.layers + 16) * unit + (8 << 30) > free
+        else:
+            drop_o = bool(self.recompute_attn_out)
+        return save_ln, drop_o
+
+    def _decide_save_ln(self, x: torch.Tensor) -> bool:
+        return self._activation_policy(x)[0]
 
     # TrainStep's overlapped gradient all-reduce: callback(tower, i) fires in backward once the gradients of every
     # block >= i are complete (tensor hook on the input of block i), for i = 0, k, 2k, ...
@@ -161,14 +178,14 @@ class Transformer(nn.Module):
     grad_bucket_blocks = 4
 
     def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool = False):
-        save_ln = self._decide_save_ln(x)
+        save_ln, drop_o = self._activation_policy(x)
         cb = self.grad_ready_callback if torch.is_grad_enabled() else None
         n_blocks = len(self.resblocks)
         for i, r in enumerate(self.resblocks):
             if cb is not None and x.requires_grad and i % self.grad_bucket_blocks == 0:
                 x.register_hook(_GradReady(cb, self, i))
             prev = self.resblocks[i - 1].mlp.c_proj.bias if i > 0 else None
-            x = r(x, batch, seq, causal, save_ln, prev, i + 1 < n_blocks)
+            x = r(x, batch, seq, causal, save_ln, prev, i + 1 < n_blocks, drop_o)
         return x
 
 

@@ -311,22 +311,23 @@ def test_patch_dropout_runs_on_device(dev):
 
 
 def test_activation_policy_save_ln_equals_recompute(dev):
-    """Keeping the LayerNorm outputs for backward (save_ln_outputs) and recomputing them are the same math."""
+    """The three activation-memory levels (keep LayerNorm outputs / recompute them / also recompute the attention
+    output) are the same math."""
     from clipa_b200.open_clip.transformer import Transformer
     meta, _ = load_golden("tiny-gap-h80", "fp32")
     grads = []
-    old = Transformer.save_ln_outputs
+    old = (Transformer.save_ln_outputs, Transformer.recompute_attn_out)
     try:
-        for policy in (True, False):
-            Transformer.save_ln_outputs = policy
+        for save_ln, drop_o in ((True, False), (False, False), (False, True)):
+            Transformer.save_ln_outputs, Transformer.recompute_attn_out = save_ln, drop_o
             model, _, _, loss = run_ours(meta, "amp_bf16", dev)
             grads.append((loss.item(), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}))
     finally:
-        Transformer.save_ln_outputs = old
-    (l0, g0), (l1, g1) = grads
-    assert l0 == l1
-    for n in g0:
-        assert rel_err(g0[n].cpu(), g1[n].cpu()) < 1e-3, n     # only fp32-atomic summation order differs
+        Transformer.save_ln_outputs, Transformer.recompute_attn_out = old
+    for l1, g1 in grads[1:]:
+        assert grads[0][0] == l1
+        for n in grads[0][1]:
+            assert rel_err(grads[0][1][n].cpu(), g1[n].cpu()) < 1e-3, n     # only fp32-atomic summation order differs
 
 
 def test_custom_text_clip_matches_clip(dev):
