@@ -2,7 +2,7 @@
   N ranks x (B/N pairs each)  ==  1 rank x B pairs
 for the loss and for every parameter gradient after the data-parallel reduction.
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/ddp_check.py
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/ddp_check.py
 """
 import json
 import os
