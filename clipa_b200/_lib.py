@@ -35,6 +35,7 @@ class GemmDesc(C.Structure):
         ("act", C.c_int32),
         ("split_k", C.c_int32),
         ("max_ctas", C.c_int32),
+        ("aux_is_derivative", C.c_int32),
     ]
 
 
@@ -105,6 +106,7 @@ _SIGNATURES = {
     "clipa_attention_f32_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                           C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "clipa_colsum_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "clipa_gemv_f32_accum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "clipa_row_lse_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
     "clipa_softmax_grad_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

@@ -368,6 +368,17 @@ softmax_grad_f32_kernel(const float* __restrict__ logits, long long ld, int M, i
   if (lane == 0) atomicAdd(dscale, acc);
 }
 
+// out[n] += sum_k v[k] * W[k*ld + n]  (vector x matrix; thread per column, k split over blockIdx.y)
+__global__ void __launch_bounds__(128)
+gemv_f32_kernel(const float* __restrict__ v, const float* __restrict__ W, long long ld, float* __restrict__ out, int K, int N) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int k0 = blockIdx.y * 64, k1 = k0 + 64 < K ? k0 + 64 : K;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int k = k0; k < k1; ++k) acc = fmaf(v[k], W[(long long)k * ld + n], acc);
+  atomicAdd(out + n, acc);
+}
+
 static inline unsigned f32_blocks(long long threads, int per_block = 256) {
   long long b = (threads + per_block - 1) / per_block;
   return (unsigned)(b < 1 ? 1 : b);
@@ -456,6 +467,15 @@ extern "C" int clipa_attention_f32_bwd(const float* qkv, const float* out, const
   count_launch();
   attn_f32_bwd_kv_kernel<<<f32_blocks(rows, kAttF32Warps), kAttF32Warps * 32, smem, s>>>(qkv, out, dout, lse, dqkv, batch, L,
                                                                                          heads, head_dim, causal, scale);
+  F32_LAUNCHED();
+}
+
+extern "C" int clipa_gemv_f32_accum(const float* v, const float* W, int64_t ld, float* out, int32_t K, int32_t N,
+                                    void* stream) {
+  CLIPA_REQUIRE(v && W && out, CLIPA_ERR_BAD_ARG, "gemv_f32_accum: null pointer");
+  CLIPA_REQUIRE(K > 0 && N > 0 && ld >= N, CLIPA_ERR_BAD_ARG, "gemv_f32_accum: bad dims");
+  dim3 grid((N + 127) / 128, (K + 63) / 64);
+  gemv_f32_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(v, W, ld, out, K, N);
   F32_LAUNCHED();
 }
 

@@ -197,6 +197,7 @@ extern "C" int clipa_gemm(const clipa_gemm_desc* d, void* stream) {
   p.residual = static_cast<const __nv_bfloat16*>(d->residual); p.ldr = d->ldr;
   p.aux = static_cast<__nv_bfloat16*>(d->aux); p.ldaux = d->ldaux;
   p.act = d->act;
+  p.aux_deriv = d->aux_is_derivative;
   p.n_per_chunk = 1;
   p.split_k = 1;
   if (d->bias) CLIPA_REQUIRE((reinterpret_cast<uintptr_t>(d->bias) & 15) == 0, CLIPA_ERR_BAD_ARG,

@@ -45,6 +45,7 @@ struct GemmParams {
   __nv_bfloat16* aux;
   long long ldaux;
   int act;
+  int aux_deriv;  // BIAS_ACT: aux receives act'(f) instead of f;  DACT: aux already holds act'(f)
   int tma_store;  // bf16 outputs leave through per-warp smem staging + TMA store (tmap_c / tmap_aux)
   // contrastive head
   float scale_log2;  // logit_scale * log2(e)
@@ -127,6 +128,19 @@ __device__ __forceinline__ float2 gelu_erf_bwd2(float2 x) {
                                 __uint_as_float(__float_as_uint(h.y) | (__float_as_uint(x.y) & 0x80000000u)));
   const float2 d = fma2(mul2(x, e), splat2(0.3989422804014327f), hs);
   return add2(d, splat2(0.5f));
+}
+// value and derivative of a pair, sharing the tail evaluation (the recompute pass of the MLP stores the derivative
+// so that the dgrad x GELU' GEMM only multiplies: its epilogue was the slowest of the block, 79 % tensor-active)
+__device__ __forceinline__ void gelu_erf_fwd_bwd2(float2 x, float2& g, float2& d) {
+  const float2 na = neg_abs_clamped2(x);
+  const float2 q = normal_tail2(na);
+  g = fma2(na, q, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+  const float2 t = mul2(mul2(x, splat2(-0.72134752044448170f)), x);
+  const float2 e = make_float2(fast_ex2(t.x), fast_ex2(t.y));
+  const float2 h = fma2(q, splat2(-1.0f), splat2(0.5f));
+  const float2 hs = make_float2(__uint_as_float(__float_as_uint(h.x) | (__float_as_uint(x.x) & 0x80000000u)),
+                                __uint_as_float(__float_as_uint(h.y) | (__float_as_uint(x.y) & 0x80000000u)));
+  d = add2(fma2(mul2(x, e), splat2(0.3989422804014327f), hs), splat2(0.5f));
 }
 __device__ __forceinline__ float act_fwd(float x, int act) {
   if (act == 0) return gelu_erf_fwd2(make_float2(x, x)).x;
@@ -256,6 +270,24 @@ __device__ __forceinline__ void chunk_store_tma(const CUtensorMap* tm, uint8_t* 
   }
 }
 
+// same staging + TMA store for a chunk that is already packed to bf16 (t[k] = columns 8k .. 8k+7 of this lane's row)
+__device__ __forceinline__ void chunk_store_tma_packed(const CUtensorMap* tm, uint8_t* sbuf, const uint4 (&t)[4], int col0,
+                                                       int row0) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) tma_store_wait_read<0>();
+  __syncwarp();
+  uint8_t* rowp = sbuf + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(rowp + ((k ^ sw) << 4)) = t[k];
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tm, sbuf, col0, row0);
+    tma_store_commit();
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[32], long long row, bool row_ok,
                                                 int col0, const float* sb, const uint4 (&side)[4],
@@ -312,6 +344,33 @@ __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[
         f[j] = lo.x; f[j + 1] = lo.y; f[j + 2] = hi.x; f[j + 3] = hi.y;
       }
     }
+    if (p.aux && p.aux_deriv) {
+      // recompute pass: aux <- act'(f) (bf16), C <- act(f); eight elements at a time so that only the packed
+      // derivative (4 registers per group) lives next to the accumulator chunk
+      uint4 dpk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float dv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const int jj = 8 * k + j;
+          if (p.act == 0) {
+            float2 g, d;
+            gelu_erf_fwd_bwd2(make_float2(f[jj], f[jj + 1]), g, d);
+            f[jj] = g.x; f[jj + 1] = g.y;
+            dv[j] = d.x; dv[j + 1] = d.y;
+          } else {
+            dv[j] = act_bwd(f[jj], p.act); dv[j + 1] = act_bwd(f[jj + 1], p.act);
+            f[jj] = act_fwd(f[jj], p.act); f[jj + 1] = act_fwd(f[jj + 1], p.act);
+          }
+        }
+        dpk[k].x = pack_bf16x2(dv[0], dv[1]); dpk[k].y = pack_bf16x2(dv[2], dv[3]);
+        dpk[k].z = pack_bf16x2(dv[4], dv[5]); dpk[k].w = pack_bf16x2(dv[6], dv[7]);
+      }
+      chunk_store_tma_packed(tm_aux, sbuf, dpk, col0, row0_warp);
+      chunk_store_tma(tm_c, sbuf, f, col0, row0_warp);
+      return;
+    }
     if (p.aux) {
       // the pre-activation is stored in bf16 and the activation is evaluated on the ROUNDED
       // value, so backward (which re-reads aux) sees the same operand
@@ -337,7 +396,14 @@ __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[
   } else if constexpr (EPI == EPI_DACT) {
     float a[32];
     unpack_bf16x32(side, a);   // rows >= M carry zeros: their result is clipped by the TMA store
-    if (p.act == 0) {
+    if (p.aux_deriv) {         // aux already holds act'(f): one packed multiply per pair
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float2 g = mul2(make_float2(f[j], f[j + 1]), make_float2(a[j], a[j + 1]));
+        f[j] = g.x;
+        f[j + 1] = g.y;
+      }
+    } else if (p.act == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
         const float2 g = mul2(make_float2(f[j], f[j + 1]), gelu_erf_bwd2(make_float2(a[j], a[j + 1])));

@@ -91,11 +91,10 @@ def _in_proj_bias_grad(dqkv: torch.Tensor, b_in: torch.Tensor, db_out: torch.Ten
       * sum_j dV_j = sum_i (sum_j P_ij) dO_i = sum_i dO_i, and dO = dx1 @ W_out, so the V part is the tiny product
         d(out_proj.bias) @ W_out (fp32, CUDA-core kernel) of a vector LayerNorm-backward has already produced;
       * only the Q third needs a pass over dqkv."""
-    from . import fp32_path
     sink = grad_sink(b_in)
     buf = sink if sink is not None else torch.zeros(3 * D, dtype=torch.float32, device=dqkv.device)
     ops.colsum_accum(dqkv[:, :D], buf[:D])
-    fp32_path.gemm_f32(db_out.view(1, D), _f32(w_out).t(), buf[2 * D:].view(1, D), accumulate=True)
+    ops.gemv_f32_accum(db_out, _f32(w_out).contiguous(), buf[2 * D:])          # += d_b_out[k] * W_out[k, :]
     if sink is not None:
         return None
     return buf if b_in.dtype == torch.float32 else buf.to(b_in.dtype)
@@ -226,14 +225,15 @@ class ResidualBlockFn(torch.autograd.Function):
         # ---- MLP: (recompute h2,) f = c_fc(h2), g = act(f)
         if h2 is None:
             h2, _, _ = ops.layernorm_fwd(x1, _f32(ln2_w), _f32(ln2_b), save_stats=False)
-        f = torch.empty(M, H4, dtype=_BF16, device=dev)
+        f = torch.empty(M, H4, dtype=_BF16, device=dev)      # receives act'(c_fc(h2)): the dgrad GEMM below only multiplies
         g = torch.empty(M, H4, dtype=_BF16, device=dev)
-        ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), aux=f, act=act)
+        ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), aux=f, act=act,
+                 aux_is_derivative=True)
         d_w_proj = _wgrad(dy, g, w_proj)
         d_b_proj = None if ctx.skip_b_proj else _bgrad(dy, b_proj)     # else: the next block's LayerNorm backward did it
         del g
         df = torch.empty(M, H4, dtype=_BF16, device=dev)
-        ops.gemm(dy, compute_copy(w_proj).t(), df, epilogue=EPI_DACT, aux=f, act=act)
+        ops.gemm(dy, compute_copy(w_proj).t(), df, epilogue=EPI_DACT, aux=f, act=act, aux_is_derivative=True)
         del f
         d_w_fc = _wgrad(df, h2, w_fc)
         d_b_fc = _bgrad(df, b_fc)

@@ -103,7 +103,7 @@ def _mat(t: torch.Tensor):
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, epilogue: int = EPI_STORE,
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
-         act: int = ACT_GELU_ERF, split_k: int = 0, max_ctas: int = 0) -> torch.Tensor:
+         act: int = ACT_GELU_ERF, split_k: int = 0, max_ctas: int = 0, aux_is_derivative: bool = False) -> torch.Tensor:
     """out[M,N] = epilogue(alpha * a[M,K] @ b[N,K]^T).  `a`/`b` may be transposed views."""
     M, K = a.shape
     N, Kb = b.shape
@@ -128,6 +128,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, epilogue: int =
     d.act = act
     d.split_k = split_k
     d.max_ctas = max_ctas
+    d.aux_is_derivative = int(aux_is_derivative)
     with _prof(("gemm", M, N, K, d.a_major, d.b_major, epilogue), 2.0 * M * N * K,
                2.0 * (M * K + N * K) + out.element_size() * M * N):
         check(_lib.lib().clipa_gemm(C.byref(d), _stream()), "clipa_gemm")
@@ -373,3 +374,12 @@ def l2_normalize_bwd(x: torch.Tensor, inv: torch.Tensor, dy: torch.Tensor) -> to
         check(_lib.lib().clipa_l2_normalize_bwd(_ptr(x), _ptr(inv), _ptr(dy), _dtype_code(dy), _ptr(dx), rows, E, _stream()),
               "clipa_l2_normalize_bwd")
     return dx
+
+
+def gemv_f32_accum(v: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> None:
+    """out[n] += sum_k v[k] * w[k, n]  (fp32, CUDA cores; w row-major [K, N])."""
+    K, N = w.shape
+    assert v.dtype == w.dtype == out.dtype == torch.float32 and v.numel() == K and out.numel() == N and w.stride(1) == 1
+    with _prof(("gemv_f32",), 2.0 * K * N, 4.0 * K * N):
+        check(_lib.lib().clipa_gemv_f32_accum(_ptr(v), _ptr(w), w.stride(0), _ptr(out), K, N, _stream()),
+              "clipa_gemv_f32_accum")

@@ -50,9 +50,9 @@ typedef enum clipa_act {
 typedef enum clipa_epilogue {
   /* C = alpha*acc (+bias[n]) (+residual[m,n]); C bf16 or f32 */
   CLIPA_EPI_STORE = 0,
-  /* f = acc + bias; C = act(f) (bf16); if aux != NULL also writes f (bf16) to aux */
+  /* f = acc + bias; C = act(f) (bf16); if aux != NULL also writes f (or, with aux_is_derivative, act'(f)) to aux */
   CLIPA_EPI_BIAS_ACT = 1,
-  /* C = acc * act'(aux[m,n])  (bf16), aux = saved pre-activation */
+  /* C = acc * act'(aux[m,n])  (bf16), aux = saved pre-activation; with aux_is_derivative C = acc * aux[m,n] */
   CLIPA_EPI_DACT = 2,
   /* C (f32) += alpha*acc with red.global.add (split-K capable; caller zero-fills or accumulates) */
   CLIPA_EPI_ATOMIC_F32 = 3
@@ -71,6 +71,7 @@ typedef struct clipa_gemm_desc {
   int32_t act;                                 /* clipa_act */
   int32_t split_k;                             /* 0/1 = none; >1 only with ATOMIC_F32; -1 = auto */
   int32_t max_ctas;                            /* 0 = one persistent CTA per SM */
+  int32_t aux_is_derivative;                   /* BIAS_ACT: aux receives act'(f) instead of f; DACT: aux holds act'(f) */
 } clipa_gemm_desc;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -234,6 +235,8 @@ int clipa_attention_f32_fwd(const float* qkv, float* out, float* lse, int32_t ba
 int clipa_attention_f32_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv,
                             int32_t batch, int32_t L, int32_t heads, int32_t head_dim, int32_t causal, void* stream);
 int clipa_colsum_f32(const float* x, int64_t ldx, float* out, int64_t rows, int32_t N, void* stream);
+/* out[n] += sum_k v[k] * W[k*ld + n]: the V third of d(in_proj_bias) = d(out_proj.bias) . W_out (bf16 path too) */
+int clipa_gemv_f32_accum(const float* v, const float* W, int64_t ld, float* out, int32_t K, int32_t N, void* stream);
 int clipa_row_lse_f32(const float* logits, int64_t ld, int32_t M, int32_t N, int32_t label_offset, float* lse,
                       float* diag, void* stream);
 int clipa_softmax_grad_f32(const float* logits, int64_t ld, int32_t M, int32_t N, int32_t label_offset,
