@@ -293,7 +293,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (col0 >= p.N) continue;  // warp-uniform
           float a[32];
           unpack_bf16x32(side, a);   // rows >= M / columns >= N arrive as zeros and are clipped by the store
-          if (p.act == 0) {
+          if (p.aux_deriv) {         // the recompute pass stored act'(f): one packed multiply per pair
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float2 r = mul2(make_float2(f[j], f[j + 1]), make_float2(a[j], a[j + 1]));
+              f[j] = r.x;
+              f[j + 1] = r.y;
+            }
+          } else if (p.act == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const float2 r = mul2(make_float2(f[j], f[j + 1]), gelu_erf_bwd2(make_float2(a[j], a[j + 1])));

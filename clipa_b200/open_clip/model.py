@@ -120,6 +120,26 @@ def _build_text_tower(embed_dim, text_cfg, quick_gelu=False, cast_dtype=None):
         attention_mask=text_cfg.attention_mask)
 
 
+def _reserve_for_later(model, text_tower, image, text) -> None:
+    """Tell each tower's activation policy what still has to fit after its own forward: the text tower runs first
+    and must leave room for the vision tower's default footprint and the contrastive head; the vision tower for the
+    head (`head_reserve_bytes`, set by TrainStep from the global batch; 1 GiB otherwise)."""
+    head = int(getattr(model, "head_reserve_bytes", 1 << 30))
+    vt = model.visual.transformer
+    gh, gw = model.visual.grid_size
+    text_tower.other_need_bytes = vt.base_need_bytes(image.shape[0] * (gh * gw + 1)) + head
+    vt.other_need_bytes = head
+
+
+def _wait_ready(image) -> None:
+    """Image batches staged on a copy stream carry their ready events (TrainStep._stage_host_images)."""
+    evs = getattr(image, "_clipa_ready", None)
+    if evs:
+        cur = torch.cuda.current_stream()
+        for ev in evs:
+            cur.wait_event(ev)
+
+
 def _l2_normalize(x: torch.Tensor) -> torch.Tensor:
     """F.normalize(dim=-1) (open_clip/model.py:240,263); the norm is taken in fp32, the result is
     rounded once to the feature dtype (bf16) that the contrastive-head GEMM consumes."""
@@ -158,6 +178,7 @@ class CLIP(nn.Module):
         self.transformer.grad_checkpointing = enable
 
     def encode_image(self, image, normalize: bool = False):
+        _wait_ready(image)
         if check_compute_precision(self) == 'fp32':
             features = fp32_path.encode_image(self.visual, image)
             return F.normalize(features, dim=-1) if normalize else features
@@ -172,8 +193,11 @@ class CLIP(nn.Module):
         return _l2_normalize(x) if normalize else x
 
     def forward(self, image, text):
-        image_features = self.encode_image(image, normalize=True)
+        # text tower first: it needs no image, so an image batch that is still on its way to the device
+        # (TrainStep stages host batches on a copy stream) hides behind it; same results either way
+        _reserve_for_later(self, self.transformer, image, text)
         text_features = self.encode_text(text, normalize=True)
+        image_features = self.encode_image(image, normalize=True)
         if self.output_dict:
             return {"image_features": image_features, "text_features": text_features,
                     "logit_scale": self.logit_scale.exp()}
@@ -207,6 +231,7 @@ class CustomTextCLIP(nn.Module):
         self.text.set_grad_checkpointing(enable)
 
     def encode_image(self, image, normalize: bool = False):
+        _wait_ready(image)
         if check_compute_precision(self) == 'fp32':
             features = fp32_path.encode_image(self.visual, image)
             return F.normalize(features, dim=-1) if normalize else features
@@ -221,8 +246,11 @@ class CustomTextCLIP(nn.Module):
         return _l2_normalize(features) if normalize else features
 
     def forward(self, image, text):
-        image_features = self.encode_image(image, normalize=True)
+        # text tower first: it needs no image, so an image batch that is still on its way to the device
+        # (TrainStep stages host batches on a copy stream) hides behind it; same results either way
+        _reserve_for_later(self, self.text.transformer, image, text)
         text_features = self.encode_text(text, normalize=True)
+        image_features = self.encode_image(image, normalize=True)
         if self.output_dict:
             return {"image_features": image_features, "text_features": text_features,
                     "logit_scale": self.logit_scale.exp()}

@@ -143,14 +143,20 @@ class Transformer(nn.Module):
         return self.resblocks[0].mlp.c_fc.weight.dtype
 
     # Activation memory policy per tower, chosen from the free HBM at forward time ('auto'), one "unit" = one
-    # [batch*L, width] bf16 tensor:
-    #   8 units / block  x, qkv (3), o, x1 + the two LayerNorm outputs     when it fits with a 16 GB margin
+    # [batch*L, width] bf16 tensor (backward adds ~10 transient units: f, g / df, dh, dx):
+    #   8 units / block  x, qkv (3), o, x1 + the two LayerNorm outputs     when it fits with a 6 GiB margin
     #   6 units / block  LayerNorm outputs recomputed in backward          default
-    #   5 units / block  attention output o recomputed too (one extra attention forward per block, ~2 % of a step)
-    #                    when even 6 units + 8 GB would not fit (ViT-H/14 at 8192 pairs per GPU: 2 GiB were left)
-    # save_ln_outputs / recompute_attn_out = True / False force a level.
+    #   5 units / block  attention output o recomputed too (one extra attention forward per block)
+    #                    when even 6 units + 3 GiB would not fit (ViT-H/14 at 8192 pairs per GPU: 2 GiB were left)
+    # `other_need_bytes` = what still has to fit AFTER this tower's forward (the other tower, the contrastive head):
+    # set by CLIP.forward.  save_ln_outputs / recompute_attn_out = True / False force a level.
     save_ln_outputs = "auto"
     recompute_attn_out = "auto"
+    other_need_bytes = 0
+
+    def base_need_bytes(self, rows: int) -> int:
+        """Bytes this tower keeps for backward at the default level (+ backward transients), for `rows` tokens."""
+        return (6 * self.layers + 10) * rows * self.width * 2
 
     def _activation_policy(self, x: torch.Tensor):
         """-> (save_ln, drop_o)"""
@@ -159,12 +165,13 @@ class Transformer(nn.Module):
         unit = x.numel() * x.element_size()
         free, _ = torch.cuda.mem_get_info(x.device)
         free += torch.cuda.memory_reserved(x.device) - torch.cuda.memory_allocated(x.device)
+        free -= self.other_need_bytes
         if self.save_ln_outputs == "auto":
-            save_ln = (8 * self.layers + 16) * unit + (16 << 30) < free   # 8 saved tensors per block + backward temporaries
+            save_ln = (8 * self.layers + 10) * unit + (6 << 30) < free
         else:
             save_ln = bool(self.save_ln_outputs)
         if self.recompute_attn_out == "auto":
-            drop_o = (not save_ln) and (6 * self.layers + 16) * unit + (8 << 30) > free
+            drop_o = (not save_ln) and (6 * self.layers + 10) * unit + (3 << 30) > free
         else:
             drop_o = bool(self.recompute_attn_out)
         return save_ln, drop_o

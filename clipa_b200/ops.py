@@ -266,10 +266,12 @@ def adamw_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, e
 # ------------------------------------------------------------------------------------------------
 # tower heads and tails (csrc/tower_io.cu)
 # ------------------------------------------------------------------------------------------------
-def preprocess_u8(images: torch.Tensor, mean, std) -> torch.Tensor:
+def preprocess_u8(images: torch.Tensor, mean, std, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """uint8 [n,3,H,W] (CUDA) -> normalised bf16, training/train.py:191-197."""
     assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[1] == 3 and images.is_contiguous()
-    out = torch.empty(images.shape, dtype=torch.bfloat16, device=images.device)
+    if out is None:
+        out = torch.empty(images.shape, dtype=torch.bfloat16, device=images.device)
+    assert out.shape == images.shape and out.dtype == torch.bfloat16 and out.is_contiguous()
     m = (C.c_float * 3)(*[float(v) for v in mean])
     s = (C.c_float * 3)(*[float(v) for v in std])
     with _prof(("preprocess_u8",), 0.0, 3.0 * images.numel()):

@@ -192,6 +192,42 @@ class TrainStep:
             images = (images.float().div_(255.0) - self._mean) * self._inv_std
         return images.to(torch.bfloat16)
 
+    _copy_stream = None
+    _ready = ()
+
+    def _stage_host_images(self, images: torch.Tensor) -> torch.Tensor:
+        """Host uint8 batch -> normalised bf16 on the device, one micro-batch at a time on a COPY stream: the H2D
+        transfer and the normalise kernel of chunk c overlap with whatever the compute stream is doing (the text
+        tower of the first chunk, the towers of earlier chunks).  Each chunk gets a ready event; the chunk's
+        slice carries it (`_clipa_ready`) and CLIP.encode_image makes the compute stream wait on it -- after the
+        text tower, which needs no image."""
+        from . import ops
+        B, mb = images.shape[0], self.micro_batch
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        side, main = self._copy_stream, torch.cuda.current_stream()
+        out = torch.empty(images.shape, dtype=torch.bfloat16, device=self.device)
+        out.record_stream(side)
+        side.wait_stream(main)            # the block behind `out` may still be in use by kernels queued on main
+        ready = []
+        with torch.cuda.stream(side):
+            for s in range(0, B, mb):
+                e = min(B, s + mb)
+                u8 = images[s:e].to(self.device, non_blocking=True)
+                ops.preprocess_u8(u8.contiguous(), self._mean_host, self._std_host, out=out[s:e])
+                ev = torch.cuda.Event()
+                ev.record(side)
+                ready.append((s, e, ev))
+        self._ready = ready
+        return out
+
+    def _chunk(self, images: torch.Tensor, s: int, e: int) -> torch.Tensor:
+        x = images[s:e]
+        evs = [ev for (a, b, ev) in self._ready if a < e and b > s]
+        if evs:
+            x._clipa_ready = evs
+        return x
+
     def zero_grad(self):
         for flat in self._flat.values():
             flat.zero_()
@@ -277,8 +313,14 @@ class TrainStep:
         overlap = self.overlap and self.fused
         if overlap and not hasattr(self, "_buckets"):
             self._setup_overlap()
+        # HBM the contrastive head will need at the end of the forward pass (gathered features, one softmax-gradient
+        # block per direction, fp32 feature gradients): the towers' activation policies leave room for it
+        E = getattr(getattr(model, "visual", None), "output_dim", 1024)
+        bg = B * self.world_size
+        model.head_reserve_bytes = (2 * bg * E * 2 + 2 * min(min(B, mb) * bg * 2, 512 << 20) + 2 * bg * E * 4
+                                    + 2 * B * E * 4 + (1 << 30))
         if B <= mb:
-            out = model(images, texts)
+            out = model(self._chunk(images, 0, B), texts)
             feats_i, feats_t, scale = self._unpack(out)
             loss = self.loss_fn(feats_i, feats_t, scale)
             self._armed = overlap            # this backward completes the gradients: buckets may go out as they finish
@@ -302,10 +344,10 @@ class TrainStep:
             for s, e in chunks[:-1]:
                 if stochastic:
                     rng.append(torch.cuda.get_rng_state(self.device))
-                a, b, _ = self._unpack(model(images[s:e], texts[s:e]))
+                a, b, _ = self._unpack(model(self._chunk(images, s, e), texts[s:e]))
                 fi.append(a)
                 ft.append(b)
-        a_last, b_last, _ = self._unpack(model(images[ls:le], texts[ls:le]))
+        a_last, b_last, _ = self._unpack(model(self._chunk(images, ls, le), texts[ls:le]))
         fi = torch.cat(fi + [a_last.detach()]).requires_grad_(True)
         ft = torch.cat(ft + [b_last.detach()]).requires_grad_(True)
         loss = self.loss_fn(fi, ft, model.logit_scale.exp())
@@ -335,8 +377,14 @@ class TrainStep:
     def step(self, images: torch.Tensor, texts: torch.Tensor) -> torch.Tensor:
         """images: uint8 or float [B_local,3,H,W]; texts: int64 [B_local, ctx].  Returns the loss
         (device scalar, no host sync)."""
-        images = self.preprocess(images)
-        texts = texts.to(self.device, non_blocking=True)
+        self._ready = ()
+        if (not images.is_cuda and images.dtype == torch.uint8 and self.device.type == "cuda" and images.dim() == 4
+                and images.shape[1] == 3):
+            texts = texts.to(self.device, non_blocking=True)      # small; first, the text tower starts with it
+            images = self._stage_host_images(images)
+        else:
+            images = self.preprocess(images)
+            texts = texts.to(self.device, non_blocking=True)
         if not (self.fused and self.step_count > 0):
             self.zero_grad()              # the fused optimizer kernel leaves the buffers cleared
         loss = self.forward_backward(images, texts)
