@@ -22,7 +22,6 @@ except Exception as e: print('  no line', e)"
 run8 "" vitl14_i81_t16_gb32k
 CLIPA_OVERLAP=0 run8 _overlap_off vitl14_i81_t16_gb32k --no-e2e
 run8 "" vitb16_i64_t16_gb16k
-CLIPA_OVERLAP=0 run8 _overlap_off vitb16_i64_t16_gb16k --no-e2e
 run8 "" vitl14_i256_t32_gb16k
 run8 "" vith14_i36_t8_gb64k --micro-batch 8192 || run8 _gradcache vith14_i36_t8_gb64k --micro-batch 4096
 timeout 600 python bench.py --global-batch 4096 --micro-batch 4096 --steps 4 --warmup 3 --no-cpu-baseline --no-library-baseline > $out/bench_1gpu_shard_same_node.json 2> $out/bench_1gpu_shard.err; echo "1gpu shard exit=$?"
