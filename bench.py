@@ -271,7 +271,7 @@ def main():
     _T.save_ln_outputs = {"auto": "auto", "on": True, "off": False}[args.save_ln]
     model.train()
     trainer = TrainStep(model, rank=rank, world_size=world, micro_batch=args.micro_batch,
-                        overlap_grad_allreduce=os.environ.get("CLIPA_OVERLAP", "1") != "0")
+                        overlap_grad_allreduce=os.environ.get("CLIPA_OVERLAP", "0") == "1")
     ctx = model.context_length
     vocab = model.vocab_size
     g = torch.Generator().manual_seed(1 + rank)

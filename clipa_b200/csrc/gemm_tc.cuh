@@ -134,13 +134,14 @@ __device__ __forceinline__ float2 gelu_erf_bwd2(float2 x) {
 __device__ __forceinline__ void gelu_erf_fwd_bwd2(float2 x, float2& g, float2& d) {
   const float2 na = neg_abs_clamped2(x);
   const float2 q = normal_tail2(na);
-  g = fma2(na, q, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
-  const float2 t = mul2(mul2(x, splat2(-0.72134752044448170f)), x);
+  g = fma2(na, q, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));   // bit-identical to gelu_erf_fwd2
+  // phi(x) = 2^(-x^2 log2(e)/2 + log2(1/sqrt(2 pi)))
+  const float2 t = fma2(mul2(x, splat2(-0.72134752044448170f)), x, splat2(-1.3257480647361593f));
   const float2 e = make_float2(fast_ex2(t.x), fast_ex2(t.y));
   const float2 h = fma2(q, splat2(-1.0f), splat2(0.5f));
   const float2 hs = make_float2(__uint_as_float(__float_as_uint(h.x) | (__float_as_uint(x.x) & 0x80000000u)),
                                 __uint_as_float(__float_as_uint(h.y) | (__float_as_uint(x.y) & 0x80000000u)));
-  d = add2(fma2(mul2(x, e), splat2(0.3989422804014327f), hs), splat2(0.5f));
+  d = fma2(x, e, add2(hs, splat2(0.5f)));                            // Phi(x) + x phi(x)
 }
 __device__ __forceinline__ float act_fwd(float x, int act) {
   if (act == 0) return gelu_erf_fwd2(make_float2(x, x)).x;
@@ -246,10 +247,13 @@ __device__ __forceinline__ const __nv_bfloat16* epi_side_ptr(const GemmParams& p
 // One 32-row x 32-column bf16 chunk: registers -> 64B-swizzled per-warp staging buffer -> TMA store.
 // The TMA engine writes whole 64-byte row segments (and clips rows >= M / columns >= N), instead of
 // 32 lanes issuing 16-byte stores to 32 different cache lines through the LSU.
+// PENDING = 1 when the warp alternates between two staging buffers (the recompute pass writes two outputs per
+// chunk): only the store issued two groups ago used this buffer, the most recent one may still be in flight.
+template <int PENDING = 0>
 __device__ __forceinline__ void chunk_store_tma(const CUtensorMap* tm, uint8_t* sbuf, const float (&f)[32],
                                                 int col0, int row0) {
   const int lane = threadIdx.x & 31;
-  if (lane == 0) tma_store_wait_read<0>();  // previous store has finished reading the staging buffer
+  if (lane == 0) tma_store_wait_read<PENDING>();  // the previous store from THIS buffer has finished reading it
   __syncwarp();
   uint8_t* rowp = sbuf + lane * 64;
   const int sw = (lane >> 1) & 3;
@@ -271,10 +275,11 @@ __device__ __forceinline__ void chunk_store_tma(const CUtensorMap* tm, uint8_t* 
 }
 
 // same staging + TMA store for a chunk that is already packed to bf16 (t[k] = columns 8k .. 8k+7 of this lane's row)
+template <int PENDING = 0>
 __device__ __forceinline__ void chunk_store_tma_packed(const CUtensorMap* tm, uint8_t* sbuf, const uint4 (&t)[4], int col0,
                                                        int row0) {
   const int lane = threadIdx.x & 31;
-  if (lane == 0) tma_store_wait_read<0>();
+  if (lane == 0) tma_store_wait_read<PENDING>();
   __syncwarp();
   uint8_t* rowp = sbuf + lane * 64;
   const int sw = (lane >> 1) & 3;
@@ -292,7 +297,7 @@ template <int EPI>
 __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[32], long long row, bool row_ok,
                                                 int col0, const float* sb, const uint4 (&side)[4],
                                                 const CUtensorMap* tm_c, const CUtensorMap* tm_aux, uint8_t* sbuf,
-                                                int row0_warp) {
+                                                int row0_warp, int aux_buf_off = 0) {
   const bool full = (col0 + 32 <= p.N);
   if constexpr (EPI == EPI_STORE) {
 #pragma unroll
@@ -348,24 +353,36 @@ __device__ __forceinline__ void epi_apply_store(const GemmParams& p, float (&f)[
       // recompute pass: aux <- act'(f) (bf16), C <- act(f); eight elements at a time so that only the packed
       // derivative (4 registers per group) lives next to the accumulator chunk
       uint4 dpk[4];
+      if (p.act == 0) {   // branch outside the loops: one straight-line block of 16 independent pairs to interleave
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float dv[8];
+        for (int k = 0; k < 4; ++k) {
+          float2 d[4];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          const int jj = 8 * k + j;
-          if (p.act == 0) {
-            float2 g, d;
-            gelu_erf_fwd_bwd2(make_float2(f[jj], f[jj + 1]), g, d);
-            f[jj] = g.x; f[jj + 1] = g.y;
-            dv[j] = d.x; dv[j + 1] = d.y;
-          } else {
-            dv[j] = act_bwd(f[jj], p.act); dv[j + 1] = act_bwd(f[jj + 1], p.act);
-            f[jj] = act_fwd(f[jj], p.act); f[jj + 1] = act_fwd(f[jj + 1], p.act);
+          for (int j = 0; j < 4; ++j) {
+            float2 g;
+            gelu_erf_fwd_bwd2(make_float2(f[8 * k + 2 * j], f[8 * k + 2 * j + 1]), g, d[j]);
+            f[8 * k + 2 * j] = g.x; f[8 * k + 2 * j + 1] = g.y;
           }
+          dpk[k].x = pack_bf16x2(d[0].x, d[0].y); dpk[k].y = pack_bf16x2(d[1].x, d[1].y);
+          dpk[k].z = pack_bf16x2(d[2].x, d[2].y); dpk[k].w = pack_bf16x2(d[3].x, d[3].y);
         }
-        dpk[k].x = pack_bf16x2(dv[0], dv[1]); dpk[k].y = pack_bf16x2(dv[2], dv[3]);
-        dpk[k].z = pack_bf16x2(dv[4], dv[5]); dpk[k].w = pack_bf16x2(dv[6], dv[7]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float dv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            dv[j] = act_bwd(f[8 * k + j], p.act);
+            f[8 * k + j] = act_fwd(f[8 * k + j], p.act);
+          }
+          dpk[k].x = pack_bf16x2(dv[0], dv[1]); dpk[k].y = pack_bf16x2(dv[2], dv[3]);
+          dpk[k].z = pack_bf16x2(dv[4], dv[5]); dpk[k].w = pack_bf16x2(dv[6], dv[7]);
+        }
+      }
+      if (aux_buf_off) {  // two staging buffers per warp: neither store waits for the one issued just before it
+        chunk_store_tma_packed<1>(tm_aux, sbuf + aux_buf_off, dpk, col0, row0_warp);
+        chunk_store_tma<1>(tm_c, sbuf, f, col0, row0_warp);
+        return;
       }
       chunk_store_tma_packed(tm_aux, sbuf, dpk, col0, row0_warp);
       chunk_store_tma(tm_c, sbuf, f, col0, row0_warp);
@@ -443,7 +460,7 @@ template <int EPI, class Release>
 __device__ __forceinline__ void epi_run_store(const GemmParams& p, uint32_t t_warp, long long row, bool row_ok,
                                               int tile_col0, int col_local0, int ncols, const float* sbias_tile,
                                               const CUtensorMap* tm_c, const CUtensorMap* tm_aux, uint8_t* sbuf,
-                                              Release release) {
+                                              Release release, int aux_buf_off = 0) {
   const int row0_warp = static_cast<int>(row) - static_cast<int>(threadIdx.x & 31);
   long long side_ld;
   const __nv_bfloat16* side_base = epi_side_ptr<EPI>(p, side_ld);
@@ -485,7 +502,7 @@ __device__ __forceinline__ void epi_run_store(const GemmParams& p, uint32_t t_wa
     }
     if (col0 >= p.N) continue;  // warp-uniform
     epi_apply_store<EPI>(p, f, row, row_ok, col0, sbias_tile + col_local0 + c * 32, side, tm_c, tm_aux, sbuf,
-                         row0_warp);
+                         row0_warp, aux_buf_off);
   }
 }
 

@@ -35,7 +35,10 @@ constexpr int kStageBytes2 = kABytes2 + kBBytes2;
 
 // Shared-memory layout of the 2-CTA kernel per epilogue type:
 //   [ A/B ring | barriers (512 B) | bias staging (2 x 256 fp32; none for DACT) | per-warp buffers ]
-// per-warp buffers: one 2 KB output staging tile (TMA store) + the DACT side-operand tiles.
+// per-warp buffers: one 2 KB output staging tile (TMA store) + the DACT side-operand tiles, or (BIAS_ACT) a second
+// staging tile for the recompute pass's act'(f) output.  The 64B-swizzled tiles need 512-byte alignment; BIAS_ACT
+// fills the 227 KB exactly enough that the 1 KB base-alignment slack is dropped (the kernel traps if the dynamic
+// shared memory base is not 1024-aligned, which it is whenever the kernel has no static shared memory).
 template <int EPI>
 struct Tc2Smem {
   static constexpr int kStages = (EPI == EPI_DACT) ? CLIPA_DACT_STAGES : 6;
@@ -43,9 +46,11 @@ struct Tc2Smem {
   static constexpr int kBarOffset = kStages * kStageBytes2;
   static constexpr int kBiasOffset = kBarOffset + 512;
   static constexpr int kBiasBytes = (EPI == EPI_DACT) ? 0 : 2048;
-  static constexpr int kStoreOffset = ((kBiasOffset + kBiasBytes + 1023) / 1024) * 1024;
-  static constexpr int kWarpBytes = 2048 * (1 + kSideBufs);
-  static constexpr int kTotal = kStoreOffset + kNumEpiWarps * kWarpBytes + 1024;
+  static constexpr int kStoreOffset = ((kBiasOffset + kBiasBytes + 511) / 512) * 512;
+  static constexpr int kAuxBufOff = (EPI == EPI_BIAS_ACT) ? 2048 : 0;   // second staging tile (0 = none)
+  static constexpr int kWarpBytes = 2048 * (1 + kSideBufs) + kAuxBufOff;
+  static constexpr int kSlack = (EPI == EPI_BIAS_ACT) ? 0 : 1024;
+  static constexpr int kTotal = kStoreOffset + kNumEpiWarps * kWarpBytes + kSlack;
   static_assert(kTotal <= 227 * 1024, "2-CTA GEMM shared memory budget");
 };
 
@@ -113,6 +118,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   using S = Tc2Smem<EPI>;
+  if constexpr (S::kSlack == 0) {
+    if (raw_addr & 1023u) __trap();   // layout without alignment slack (see Tc2Smem)
+  }
   constexpr int kStages2 = S::kStages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);   // used in the leader
   uint64_t* empty_bar = full_bar + kStages2;                              // per CTA
@@ -336,7 +344,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                            tc_fence_before();
                            __syncwarp();
                            if (lane == 0) mbar_arrive_cluster(leader_addr(smem_u32(&tmem_empty[acc])));
-                         });
+                         }, S::kAuxBufOff);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     }

@@ -42,7 +42,7 @@ class TrainStep:
                  wd: float = 0.2, micro_batch: int = 4096, local_loss: bool = True,
                  gather_with_grad: bool = True, image_mean=None, image_std=None,
                  grad_clip_norm: Optional[float] = None, fused_optimizer: bool = True,
-                 reference_accum_logit_scale: bool = True, overlap_grad_allreduce: bool = True,
+                 reference_accum_logit_scale: bool = True, overlap_grad_allreduce: bool = False,
                  allreduce_bucket_blocks: int = 4):
         self.model = model
         self.rank, self.world_size = rank, world_size

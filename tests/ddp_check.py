@@ -42,9 +42,10 @@ def main():
     images, text = make_inputs(cfg, B, 99)
     bl = B // world
     # --- N-rank step (micro-batch smaller than the local batch -> also exercises the GradCache path)
-    for mb in (bl, bl // 2):
+    for mb, overlap in ((bl, False), (bl // 2, False), (bl, True), (bl // 2, True)):
         # single-pass logit_scale gradient on both sides (the reference's accumulation loop counts it once per chunk)
-        ts = TrainStep(model, rank=rank, world_size=world, micro_batch=mb, reference_accum_logit_scale=False)
+        ts = TrainStep(model, rank=rank, world_size=world, micro_batch=mb, reference_accum_logit_scale=False,
+                       overlap_grad_allreduce=overlap, allreduce_bucket_blocks=1)
         ts.zero_grad()
         loss = ts.forward_backward(ts.preprocess(images[rank * bl:(rank + 1) * bl]), text[rank * bl:(rank + 1) * bl].to(dev))
         ts._allreduce_grads()
@@ -62,7 +63,7 @@ def main():
             err = ((g1 - gN).norm() / g1.norm().clamp_min(1e-12)).item()
             worst = max(worst, err)
         if rank == 0:
-            print(f"[ddp_check] world={world} micro_batch={mb}: mean-over-ranks loss {lsum.item() / world:.6f} vs "
+            print(f"[ddp_check] world={world} micro_batch={mb} overlap={overlap}: mean-over-ranks loss {lsum.item() / world:.6f} vs "
                   f"single-rank {loss1.item():.6f}; worst parameter-gradient rel err {worst:.3e}", flush=True)
         assert abs(lsum.item() / world - loss1.item()) / loss1.item() < 2e-3
         assert worst < 5e-2, worst   # bf16 activations; different micro-batching changes rounding only

@@ -65,7 +65,7 @@ def _worker(rank, world, port, out_dir):
         net.transformer = Transformer(width=64, layers=5, heads=1)
         net.logit_scale = torch.nn.Parameter(torch.tensor(1.0))
         ts2 = TrainStep(net, rank=rank, world_size=world, micro_batch=4, image_mean=(0., 0., 0.), image_std=(1., 1., 1.),
-                        allreduce_bucket_blocks=2)
+                        allreduce_bucket_blocks=2, overlap_grad_allreduce=True)
         assert ts2.fused and ts2.overlap
         ts2._setup_overlap()
         assert sorted(b0 for (_, b0) in ts2._buckets) == [0, 2, 4]
