@@ -18,11 +18,20 @@
 //               smem; then the O_j half-row from TMEM: o = o * alpha + O_j in REGISTERS (no TMEM
 //               read-modify-write, no correction warps); after the last key tile o / l -> HBM.
 // HBM traffic per (sample, head): Q, O once; K, V once per query tile (T times, L2 hits).
+#include <cstdlib>
 #include <type_traits>
 
 #include "attn_common.cuh"
 #include "host_common.h"
 #include "ptx.cuh"
+
+// experiment switches of the forward softmax workers (A/B builds: CLIPA_B200_NVCC_FLAGS="-DCLIPA_FLASH_MASKMODE=0")
+#ifndef CLIPA_FLASH_MASKMODE
+#define CLIPA_FLASH_MASKMODE 2     // 0: per-element key test on every chunk of a masked warp; 1: warp-uniform chunk kinds (votes); 2: uniform, plain tiles only
+#endif
+#ifndef CLIPA_FLASH_MATHMODE
+#define CLIPA_FLASH_MATHMODE 1     // 0: scalar FFMA / FADD; 1: packed fp32 (FFMA2 / FADD2)
+#endif
 
 namespace clipa {
 
@@ -275,8 +284,13 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;     // column half of the score row / of the output row
     const int row = q * 32 + lane;
-    const bool active = q * 32 < Rt;      // warp-uniform and equal for the two halves of a quarter
+    const bool warp_active = q * 32 < Rt;  // warp-uniform and equal for the two halves of a quarter
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    // The loop is instantiated twice: warps whose 32 rows lie beyond the tile only keep the barrier protocol going.
+    // With a runtime `if (active)` around the math, the running output row became a phi of {updated, untouched}
+    // that ptxas placed in the TMEM-load registers: 64 register moves per step in the active warps.
+    auto run_workers = [&](auto act_tag) {
+    constexpr bool active = decltype(act_tag)::value;
     const int hsplit = ((p.npad + 31) >> 5) << 4;                // 96 keys: 48 + 48
     const int c_begin = half * hsplit;
     const int c_end = min(p.npad, c_begin + hsplit);
@@ -311,28 +325,37 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
         for (int c3 = 0; c3 < NCH; ++c3)
           if (c_begin + 16 * c3 < c_end) tmem_ld_32x16(t_row + s * 128 + c_begin + 16 * c3, v[c3]);
         tmem_ld_wait();
+        // per 16-column chunk, decided for the whole warp: 0 = every key valid, 1 = some masked, 2 = none valid.  Only the chunk
+        // that straddles a boundary pays for the per-element test (2 ISETP + 2 FSEL each: with the test on every
+        // element the masked half-row warps ran 1.6x the instructions of the others and set the pace of the tile).
+        int kind[NCH];
+#pragma unroll
+        for (int c3 = 0; c3 < NCH; ++c3) {
+          const int base = c_begin + 16 * c3;
+#if CLIPA_FLASH_MASKMODE == 0
+          kind[c3] = need_mask ? 1 : 0;                               // every chunk of a masked warp pays the test
+#elif CLIPA_FLASH_MASKMODE == 2
+          // plain (non-causal, unpacked) tiles: [0, hi) is the same for every row, so only the chunk that holds
+          // `hi` is tested -- decided without votes, and never "skip", so the exp pass stays one straight block
+          kind[c3] = (!CAUSAL && G == 1) ? ((need_mask && base + 16 > hi) ? 1 : 0) : (need_mask ? 1 : 0);
+#else
+          const bool full = !need_mask || (base >= lo && base + 16 <= hi);
+          const bool none = need_mask && (base >= hi || base + 16 <= lo);
+          kind[c3] = __all_sync(0xffffffffu, full) ? 0 : (__all_sync(0xffffffffu, none) ? 2 : 1);   // warp-uniform
+#endif
+        }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (need_mask) {
 #pragma unroll
-          for (int c3 = 0; c3 < NCH; ++c3) {
-            if (c_begin + 16 * c3 < c_end) {
+        for (int c3 = 0; c3 < NCH; ++c3) {
+          if (c_begin + 16 * c3 < c_end && kind[c3] != 2) {
+            if (kind[c3] == 1) {
+              const int rel_lo = lo - (c_begin + 16 * c3), rel_hi = hi - (c_begin + 16 * c3);
 #pragma unroll
-              for (int jj = 0; jj < 16; ++jj) {
-                float x = __uint_as_float(v[c3][jj]);
-                const int col = c_begin + 16 * c3 + jj;
-                if (col >= hi || col < lo) x = -INFINITY;
-                v[c3][jj] = __float_as_uint(x);
-                mx[jj & 3] = fmaxf(mx[jj & 3], x);
-              }
+              for (int jj = 0; jj < 16; ++jj)
+                if (jj >= rel_hi || jj < rel_lo) v[c3][jj] = __float_as_uint(-INFINITY);
             }
-          }
-        } else {
 #pragma unroll
-          for (int c3 = 0; c3 < NCH; ++c3) {
-            if (c_begin + 16 * c3 < c_end) {
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) mx[jj & 3] = fmaxf(mx[jj & 3], __uint_as_float(v[c3][jj]));
-            }
+            for (int jj = 0; jj < 16; ++jj) mx[jj & 3] = fmaxf(mx[jj & 3], __uint_as_float(v[c3][jj]));
           }
         }
         const float mine = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
@@ -343,23 +366,45 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
         alpha = (m == -INFINITY) ? 0.f : ex2_approx(ms - ms_new);
         m = m_new;
         ms = ms_new;
-        float sm[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 sm01 = make_float2(0.f, 0.f), sm23 = make_float2(0.f, 0.f);
+        const float2 sc2 = splat2(p.scale_log2), nms2 = splat2(-ms);
         uint8_t* pbuf = smem + Sm::kPOff + s * kTcPBytes;
 #pragma unroll
         for (int c3 = 0; c3 < NCH; ++c3) {
           if (c_begin + 16 * c3 < c_end) {
             float pr[16];
+            if (kind[c3] != 2) {
+#if CLIPA_FLASH_MATHMODE == 0
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              pr[jj] = ex2_approx(fmaf(__uint_as_float(v[c3][jj]), p.scale_log2, -ms));   // exp2(-inf) = 0
-              sm[jj & 3] += pr[jj];
+              for (int jj = 0; jj < 16; jj += 4) {
+                pr[jj] = ex2_approx(fmaf(__uint_as_float(v[c3][jj]), p.scale_log2, -ms));
+                pr[jj + 1] = ex2_approx(fmaf(__uint_as_float(v[c3][jj + 1]), p.scale_log2, -ms));
+                pr[jj + 2] = ex2_approx(fmaf(__uint_as_float(v[c3][jj + 2]), p.scale_log2, -ms));
+                pr[jj + 3] = ex2_approx(fmaf(__uint_as_float(v[c3][jj + 3]), p.scale_log2, -ms));
+                sm01.x += pr[jj]; sm01.y += pr[jj + 1]; sm23.x += pr[jj + 2]; sm23.y += pr[jj + 3];
+              }
+#else
+#pragma unroll
+              for (int jj = 0; jj < 16; jj += 4) {     // packed fp32: one FFMA2 / FADD2 per pair; exp2(-inf) = 0
+                const float2 t0 = fma2(make_float2(__uint_as_float(v[c3][jj]), __uint_as_float(v[c3][jj + 1])), sc2, nms2);
+                const float2 t1 = fma2(make_float2(__uint_as_float(v[c3][jj + 2]), __uint_as_float(v[c3][jj + 3])), sc2, nms2);
+                pr[jj] = ex2_approx(t0.x); pr[jj + 1] = ex2_approx(t0.y);
+                pr[jj + 2] = ex2_approx(t1.x); pr[jj + 3] = ex2_approx(t1.y);
+                sm01 = add2(sm01, make_float2(pr[jj], pr[jj + 1]));
+                sm23 = add2(sm23, make_float2(pr[jj + 2], pr[jj + 3]));
+              }
+#endif
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) pr[jj] = 0.f;
             }
 #pragma unroll
             for (int g8 = 0; g8 < 2; ++g8)
               *reinterpret_cast<uint4*>(pbuf + p_tile_off(row, ((c_begin + 16 * c3) >> 3) + g8)) = pack8_bf16(pr + 8 * g8);
           }
         }
-        l = fmaf(l, alpha, (sm[0] + sm[1]) + (sm[2] + sm[3]));
+        const float2 sm = add2(sm01, sm23);
+        l = fmaf(l, alpha, sm.x + sm.y);
         fence_proxy_async_smem();
       }
       tc_fence_before();
@@ -397,12 +442,14 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
           tmem_ld_32x16(t_o + 64, t2);
           tmem_ld_wait();
 #pragma unroll
-          for (int d = 0; d < 16; ++d) o_rem[d] = fmaf(o_rem[d], alpha_cur, __uint_as_float(t2[d]));
+          for (int d = 0; d < 16; d += 2)
+            fma2_acc(o_rem[d], o_rem[d + 1], alpha_cur, __uint_as_float(t2[d]), __uint_as_float(t2[d + 1]));
         } else {
           tmem_ld_wait();
         }
 #pragma unroll
-        for (int d = 0; d < 32; ++d) o_main[d] = fmaf(o_main[d], alpha_cur, __uint_as_float(t[d]));
+        for (int d = 0; d < 32; d += 2)
+          fma2_acc(o_main[d], o_main[d + 1], alpha_cur, __uint_as_float(t[d]), __uint_as_float(t[d + 1]));
       }
       tc_fence_before();
       __syncwarp();
@@ -438,6 +485,8 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
       alpha_cur = alpha_next;
       if (co.advance() && co.it < n_local) decode(co.it, co.n, co.h, co.i);
     }
+    };   // run_workers
+    if (warp_active) run_workers(std::true_type{}); else run_workers(std::false_type{});
   }
 
   tc_fence_before();
@@ -536,7 +585,9 @@ struct FlashBwdSmem {
   static constexpr int kKvOff = kNumPds * kPdsBytes;           //   last dS atom lands in the operand slots below
   static constexpr int kQdOff = kKvOff + 4 * Tl::kOpBytes;     // 2 slots x {K, V}, then 2 slots x {Q, dO, O}
   static constexpr int kBarOff = kQdOff + 6 * Tl::kOpBytes;
-  static constexpr int kTotal = kBarOff + 256 + 1024;
+  static constexpr int kDcTiles = 8;                           // delta_i cache: [column half][query tile][row] fp32
+  static constexpr int kDcOff = kBarOff + 256;
+  static constexpr int kTotal = kDcOff + 2 * kDcTiles * 128 * 4 + 1024;
   static_assert(kTotal <= 227 * 1024, "flash attention backward shared memory budget");
 };
 
@@ -547,6 +598,7 @@ struct FlashBwdParams {
   int L, H, batch;
   int T, Rt, npad;
   int G;                 // samples packed per tile (see FlashParams)
+  int dq_tmem;           // dQ_i of all T query tiles stay in TMEM across the key tiles (no scratch round trip)
   float scale;
 };
 
@@ -643,7 +695,15 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr uint32_t kColS = 0, kColDp = 128, kColDq = 256, kColDk = 256 + HD, kColDv = 256 + 2 * HD;
+  // TMEM columns.  Default: S 0, dP 128, one dQ tile 256, dK 256+HD, dV 256+2HD (dQ partial sums over the key tiles
+  // go through the fp32 scratch).  dq_tmem (T*HD + 2*npad + 2*HD <= 512, e.g. L = 257 at head_dim 64): S 0, dP npad,
+  // dQ_i at 2*npad + i*HD for every query tile of the item -- accumulated by the MMAs over j, read once --, then dK, dV.
+  constexpr uint32_t kColS = 0;
+  const bool dqt = p.dq_tmem != 0;
+  const uint32_t kColDp = dqt ? (uint32_t)p.npad : 128u;
+  const uint32_t kColDq = dqt ? 2u * (uint32_t)p.npad : 256u;
+  const uint32_t kColDk = dqt ? kColDq + (uint32_t)(T * HD) : 256u + HD;
+  const uint32_t kColDv = kColDk + HD;
 
   const int n_local = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int K = n_local * T * T;   // steps: (item, key tile j, query tile i), i fastest
@@ -737,10 +797,11 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
         for (int kk = 0; kk < ksteps; ++kk) {
           // contraction over keys: A = dS K-major, B = K_j consumed MN-major; fresh dQ tile
           const uint64_t a_ds = make_smem_desc_sw128(dsa + (kk >> 2) * kPAtom + (kk & 3) * 32, 16, 1024);
-          const uint32_t acc = kk > 0 ? 1u : 0u;
-          if (im.issue) umma_bf16(tmem_base + kColDq, a_ds, make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q64, acc);
+          const uint32_t acc = (kk > 0 || (dqt && cg.j > 0)) ? 1u : 0u;
+          const uint32_t d_q = tmem_base + kColDq + (dqt ? (uint32_t)(cg.i * HD) : 0u);
+          if (im.issue) umma_bf16(d_q, a_ds, make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q64, acc);
           if constexpr (HD != 64)
-            if (im.issue) umma_bf16(tmem_base + kColDq + 64, a_ds,
+            if (im.issue) umma_bf16(d_q + 64, a_ds,
                                     make_smem_desc_sw32(ka + Tl::kMainBytes + kk * 512, 256, 256), idesc_q16, acc);
         }
         if (im.issue) umma_commit(grad_full);
@@ -772,6 +833,8 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
     const int c_begin = half * hsplit;
     const int c_end = min(p.npad, c_begin + hsplit);
     float* scr = p.scratch + (long long)blockIdx.x * T * Rt * HD;
+    float* dcache = reinterpret_cast<float*>(smem + Sm::kDcOff);
+    const bool delta_cached = T > 1 && T <= Sm::kDcTiles;
     // packed tiles: this row's sample within the tile and its first row / key column
     const int psample = G > 1 ? min(row, Rt - 1) / L : 0;
     const int plo = psample * L;
@@ -829,8 +892,16 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
       }
       // delta_i = sum_d dO_id * O_id from the swizzled smem tiles (same swizzle in both tiles, so any
       // consistent chunk order gives matching pairs)
-      mbar_wait(&qd_full[s], (k >> 1) & 1);
+      // delta_i does not depend on the key tile: computed in the item's first pass over the query tiles (j == 0) and
+      // kept in shared memory, one slot per (column half, query tile, row) so that the reader is the thread that
+      // wrote it (recomputed for every j it was 140 of the ~1000 instructions of a step: two LDS.128 + 16 unpacks
+      // + 8 FFMA per 8 head dimensions, by both threads of the row)
       float delta = 0.f;
+      float* dslot = dcache + (half * Sm::kDcTiles + cs.i) * 128 + row;
+      if (delta_cached && cs.j > 0) {
+        delta = *dslot;
+      } else {
+      mbar_wait(&qd_full[s], (k >> 1) & 1);
       if (row_ok && c_begin < c_end) {
         const uint8_t* dot = smem + Sm::kQdOff + s * 3 * Tl::kOpBytes + Tl::kOpBytes;
         const uint8_t* ot = dot + Tl::kOpBytes;
@@ -857,6 +928,8 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
         }
         delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
       }
+      if (delta_cached) *dslot = delta;
+      }
       mbar_wait(sdp_full, k & 1);
       tc_fence_after();
       const float lse2 = lse_raw * 1.4426950408889634f;
@@ -869,15 +942,21 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
         uint8_t* p_buf = smem + Sm::kPdsOff + pds_buf(k) * Sm::kPdsBytes;
         uint8_t* ds_buf = p_buf + 2 * kPAtom;
         for (int c = c_begin; c < c_end; c += 16) {
-          uint32_t sv[16], dv[16];
-          tmem_ld_32x16(t_row + kColS + c, sv);
-          tmem_ld_32x16(t_row + kColDp + c, dv);
-          tmem_ld_wait();
           float pr[16], ds[16];
-          if (row_ok && c >= lo && c + 16 <= hi)
-            attn_bwd_chunk16<false>(sv, dv, scale_log2, lse2, p.scale, nds, c, lo, hi, row_ok, pr, ds);
-          else
-            attn_bwd_chunk16<true>(sv, dv, scale_log2, lse2, p.scale, nds, c, lo, hi, row_ok, pr, ds);
+          const int kind = attn_chunk_kind(row_ok, c, lo, hi);
+          if (kind != 2) {
+            uint32_t sv[16], dv[16];
+            tmem_ld_32x16(t_row + kColS + c, sv);
+            tmem_ld_32x16(t_row + kColDp + c, dv);
+            tmem_ld_wait();
+            if (kind == 0)
+              attn_bwd_chunk16<false>(sv, dv, scale_log2, lse2, p.scale, nds, c, lo, hi, row_ok, pr, ds);
+            else
+              attn_bwd_chunk16<true>(sv, dv, scale_log2, lse2, p.scale, nds, c, lo, hi, row_ok, pr, ds);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pr[j] = ds[j] = 0.f;
+          }
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
             const uint32_t off = fb_tile_off(row, (c >> 3) + g8);
@@ -902,7 +981,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
       float* srow = scr + (long long)(i * Rt + row) * HD;
       float acc[32], acc2[16];
       const bool dq_ok = warp_stores && row_ok;
-      if (!first_j && dq_ok) {                     // issued before the wait: L2 latency hides behind the MMAs
+      if (!dqt && !first_j && dq_ok) {             // issued before the wait: L2 latency hides behind the MMAs
 #pragma unroll
         for (int d4 = 0; d4 < 8; ++d4)
           *reinterpret_cast<float4*>(acc + 4 * d4) = *reinterpret_cast<const float4*>(srow + half * 32 + 4 * d4);
@@ -916,14 +995,16 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
       tc_fence_after();
       if (warp_stores) {
         __nv_bfloat16* qrow = p.dqkv + ((long long)n * L + i * Rt + row) * pitch + h * HD;
-        {
+        const uint32_t t_dq = t_row + kColDq + (dqt ? (uint32_t)(i * HD) : 0u);
+        const bool add_acc = !dqt && !first_j;
+        if (!dqt || last_j) {
           uint32_t v[32];
-          tmem_ld_32x32(t_row + kColDq + half * 32, v);
+          tmem_ld_32x32(t_dq + half * 32, v);
           tmem_ld_wait();
           if (dq_ok) {
             float f[32];
 #pragma unroll
-            for (int d = 0; d < 32; ++d) f[d] = __uint_as_float(v[d]) + (first_j ? 0.f : acc[d]);
+            for (int d = 0; d < 32; ++d) f[d] = __uint_as_float(v[d]) + (add_acc ? acc[d] : 0.f);
             if (last_j) {
 #pragma unroll
               for (int g8 = 0; g8 < 4; ++g8) reinterpret_cast<uint4*>(qrow + half * 32)[g8] = pack8_bf16(f + 8 * g8);
@@ -934,14 +1015,14 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
             }
           }
         }
-        if (HD != 64 && half == 0) {
+        if (HD != 64 && half == 0 && (!dqt || last_j)) {
           uint32_t v[16];
-          tmem_ld_32x16(t_row + kColDq + 64, v);
+          tmem_ld_32x16(t_dq + 64, v);
           tmem_ld_wait();
           if (dq_ok) {
             float f[16];
 #pragma unroll
-            for (int d = 0; d < 16; ++d) f[d] = __uint_as_float(v[d]) + (first_j ? 0.f : acc2[d]);
+            for (int d = 0; d < 16; ++d) f[d] = __uint_as_float(v[d]) + (add_acc ? acc2[d] : 0.f);
             if (last_j) {
 #pragma unroll
               for (int g8 = 0; g8 < 2; ++g8) reinterpret_cast<uint4*>(qrow + 64)[g8] = pack8_bf16(f + 8 * g8);
@@ -991,6 +1072,12 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
   }
 }
 
+// CLIPA_FLASH_DQ_TMEM=0 keeps the scratch path for every shape (A/B)
+static bool flash_dq_tmem_enabled() {
+  static const bool on = [] { const char* e = getenv("CLIPA_FLASH_DQ_TMEM"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <int HD>
 static int launch_bwd_flash(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                             void* workspace, long long workspace_bytes, int batch, int L, int H, int causal,
@@ -1005,7 +1092,8 @@ static int launch_bwd_flash(const void* qkv, const void* out, const void* dout, 
   const long long total = (long long)((batch + p.G - 1) / p.G) * H;
   int grid = num_sms();
   if (grid > total) grid = (int)total;
-  const long long need = p.T > 1 ? (long long)grid * p.T * p.Rt * HD * 4 : 0;
+  p.dq_tmem = (flash_dq_tmem_enabled() && p.T > 1 && p.T * HD + 2 * p.npad + 2 * HD <= 512) ? 1 : 0;
+  const long long need = (p.T > 1 && !p.dq_tmem) ? (long long)grid * p.T * p.Rt * HD * 4 : 0;
   CLIPA_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need), CLIPA_ERR_BAD_ARG,
                 "attention_bwd: L=%d needs a %lld-byte workspace (clipa_attention_bwd_workspace), got %lld", L, need,
                 workspace_bytes);

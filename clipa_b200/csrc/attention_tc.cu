@@ -621,15 +621,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_co
       }
       if (warp_writes) {
         for (int c = c_begin; c < c_end; c += 16) {
-          uint32_t sv[16], dv[16];
-          tmem_ld_32x16(t_row + kColS + c, sv);
-          tmem_ld_32x16(t_row + kColDp + c, dv);
-          tmem_ld_wait();
           float pr[16], ds[16];
-          if (row_ok && c >= mlo && c + 16 <= span.hi)
-            attn_bwd_chunk16<false>(sv, dv, scale_log2, lse2, p.scale, nds, c, mlo, span.hi, row_ok, pr, ds);
-          else
-            attn_bwd_chunk16<true>(sv, dv, scale_log2, lse2, p.scale, nds, c, mlo, span.hi, row_ok, pr, ds);
+          const int kind = attn_chunk_kind(row_ok, c, mlo, span.hi);
+          if (kind != 2) {
+            uint32_t sv[16], dv[16];
+            tmem_ld_32x16(t_row + kColS + c, sv);
+            tmem_ld_32x16(t_row + kColDp + c, dv);
+            tmem_ld_wait();
+            if (kind == 0)
+              attn_bwd_chunk16<false>(sv, dv, scale_log2, lse2, p.scale, nds, c, mlo, span.hi, row_ok, pr, ds);
+            else
+              attn_bwd_chunk16<true>(sv, dv, scale_log2, lse2, p.scale, nds, c, mlo, span.hi, row_ok, pr, ds);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pr[j] = ds[j] = 0.f;
+          }
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
             const uint32_t off = p_tile_off(row, (c >> 3) + g8);
@@ -864,15 +870,21 @@ attn_bwd_tc_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         uint8_t* p_buf = smem + kPPOff + s * 2 * kPPds;
         uint8_t* ds_buf = p_buf + kPPds;
         for (int c = c_begin; c < c_end; c += 16) {
-          uint32_t sv[16], dv[16];
-          tmem_ld_32x16(t_row + kColS + c, sv);
-          tmem_ld_32x16(t_row + kColDp + c, dv);
-          tmem_ld_wait();
           float pr[16], ds[16];
-          if (row_ok && c + 16 <= hi)
-            attn_bwd_chunk16<false>(sv, dv, scale_log2, lse2, p.scale, nds, c, 0, hi, row_ok, pr, ds);
-          else
-            attn_bwd_chunk16<true>(sv, dv, scale_log2, lse2, p.scale, nds, c, 0, hi, row_ok, pr, ds);
+          const int kind = attn_chunk_kind(row_ok, c, 0, hi);
+          if (kind != 2) {
+            uint32_t sv[16], dv[16];
+            tmem_ld_32x16(t_row + kColS + c, sv);
+            tmem_ld_32x16(t_row + kColDp + c, dv);
+            tmem_ld_wait();
+            if (kind == 0)
+              attn_bwd_chunk16<false>(sv, dv, scale_log2, lse2, p.scale, nds, c, 0, hi, row_ok, pr, ds);
+            else
+              attn_bwd_chunk16<true>(sv, dv, scale_log2, lse2, p.scale, nds, c, 0, hi, row_ok, pr, ds);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pr[j] = ds[j] = 0.f;
+          }
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
             const uint32_t off = p96_tile_off(row, (c >> 3) + g8);

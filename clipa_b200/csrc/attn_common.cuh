@@ -32,6 +32,15 @@ __device__ __forceinline__ uint32_t p_tile_off(int row, int chunk) {
 // on the packed-fp32 pipe (one FFMA2 for the exponent pair, one FFMA2 + one FMUL2 for the dS pair).  MASKED: columns
 // outside [lo, hi) (padding, other samples of a packed tile, causal future) and rows that do not exist give P = dS = 0;
 // chunks that lie inside the valid range take the predicate-free variant.
+// Warp-uniform classification of one 16-key chunk (call with all 32 lanes): 0 = no lane needs the mask, 2 = no lane
+// has a valid key in it (block-diagonal packed tiles, rows beyond the sequence), 1 = mixed.  Decided per lane, a warp
+// whose rows straddle the end of the sequence (or two packed samples) executed BOTH variants of every chunk.
+__device__ __forceinline__ int attn_chunk_kind(bool row_ok, int c, int lo, int hi) {
+  const bool full = row_ok && c >= lo && c + 16 <= hi;
+  const bool none = !row_ok || c >= hi || c + 16 <= lo;
+  return __all_sync(0xffffffffu, full) ? 0 : (__all_sync(0xffffffffu, none) ? 2 : 1);
+}
+
 template <bool MASKED>
 __device__ __forceinline__ void attn_bwd_chunk16(const uint32_t (&sv)[16], const uint32_t (&dv)[16], float scale_log2,
                                                  float lse2, float scale, float nds, int c, int lo, int hi, bool row_ok,

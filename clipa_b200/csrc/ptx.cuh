@@ -263,6 +263,14 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   return d;
 }
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+// (x, y) = (x, y) * a + (cx, cy), accumulator operands tied to the result registers
+__device__ __forceinline__ void fma2_acc(float& x, float& y, float a, float cx, float cy) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %2};\n\tmov.b64 rc, {%3, %4};\n\t"
+      "fma.rn.f32x2 ra, ra, rb, rc;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(x), "+f"(y)
+      : "f"(a), "f"(cx), "f"(cy));
+}
 
 // ----------------------------------------------------------------------------------------------
 // Issue mode of the single-thread instruction streams (tcgen05.mma / commit).

@@ -44,7 +44,7 @@ def accuracy(output: torch.Tensor, target: torch.Tensor, topk: Tuple[int, ...] =
     """zero_shot.py:49-52."""
     pred = output.topk(max(topk), 1, True, True)[1].t()
     correct = pred.eq(target.view(1, -1).expand_as(pred))
-    return [float(correct[:k].reshape(-1).float().sum(0, keepdim=True).cpu().numpy()) for k in topk]
+    return [float(correct[:k].reshape(-1).float().sum().item()) for k in topk]
 
 
 @torch.no_grad()
