@@ -28,19 +28,22 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-# model, image px, pos-embed, global batch, algorithmic fwd+bwd GFLOP per pair
+# model, image px, pos-embed, global batch, algorithmic fwd+bwd GFLOP per pair;
+# micro = (largest per-GPU batch that runs as ONE plain forward/backward in 180 GB, chunk size when the per-GPU batch
+# is larger than that and the GradCache schedule is needed anyway: small enough that the blocks keep their MLP
+# activations, see Transformer._activation_policy)
 WORKLOADS = {
     "vitl14_i81_t16_gb32k": dict(model="ViT-L-14-CL16", image=126, pos="sin_cos_2d", global_batch=32768,
-                                 gflop_per_pair=159.35, baseline_config="configs[2]"),
+                                 gflop_per_pair=159.35, baseline_config="configs[2]", micro=(4096, 2048)),
     "vitb16_i64_t16_gb16k": dict(model="ViT-B-16-CL16", image=128, pos="sin_cos_2d", global_batch=16384,
-                                 gflop_per_pair=37.57, baseline_config="configs[1]"),
+                                 gflop_per_pair=37.57, baseline_config="configs[1]", micro=(8192, 8192)),
     "vitl14_i256_t32_gb16k": dict(model="ViT-L-14-CL32", image=224, pos="learnable", global_batch=16384,
-                                  gflop_per_pair=502.65, baseline_config="configs[3]"),
+                                  gflop_per_pair=502.65, baseline_config="configs[3]", micro=(2048, 1024)),
     "vith14_i36_t8_gb64k": dict(model="ViT-H-14-CL8-SyntaxMask-GAP", image=84, pos="sin_cos_2d",
-                                global_batch=65536, gflop_per_pair=155.84, baseline_config="configs[4]"),
+                                global_batch=65536, gflop_per_pair=155.84, baseline_config="configs[4]", micro=(8192, 4096)),
     # small plumbing case for smoke runs of this script
     "vitb32_i36_t16_gb256": dict(model="ViT-B-32-CL16", image=192, pos="sin_cos_2d", global_batch=256,
-                                 gflop_per_pair=23.16, baseline_config="configs[0] shape, batch 256"),
+                                 gflop_per_pair=23.16, baseline_config="configs[0] shape, batch 256", micro=(256, 128)),
 }
 METRIC = "image-text pairs/sec at ViT-L/14, global batch 32k, 1/2/4/8 B200"
 
@@ -221,7 +224,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vitl14_i81_t16_gb32k", choices=list(WORKLOADS))
     ap.add_argument("--global-batch", type=int, default=None)
-    ap.add_argument("--micro-batch", type=int, default=4096)
+    ap.add_argument("--micro-batch", type=int, default=0,
+                    help="pairs per forward/backward chunk (0 = auto from the workload's `micro` pair: the whole per-GPU "
+                         "batch when it fits one plain step, else the GradCache chunk size at which the blocks keep "
+                         "their MLP activations and backward skips the c_fc recompute GEMM)")
+    ap.add_argument("--keep-mlp", default="auto", help="blocks that keep their MLP activations (auto | integer)")
     ap.add_argument("--precision", default="amp_bf16", choices=["amp_bf16", "bf16"])
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -269,6 +276,10 @@ def main():
             dist.broadcast(p.data, 0)
     from clipa_b200.open_clip.transformer import Transformer as _T
     _T.save_ln_outputs = {"auto": "auto", "on": True, "off": False}[args.save_ln]
+    _T.keep_mlp_blocks = "auto" if args.keep_mlp == "auto" else int(args.keep_mlp)
+    if args.micro_batch <= 0:
+        plain, chunk = wl["micro"]
+        args.micro_batch = plain if bl <= plain else chunk
     model.train()
     trainer = TrainStep(model, rank=rank, world_size=world, micro_batch=args.micro_batch,
                         overlap_grad_allreduce=os.environ.get("CLIPA_OVERLAP", "0") == "1")
@@ -368,6 +379,8 @@ def main():
                        "loss_last": float(last_loss),
                        "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
                        "save_ln_outputs": str(type(model.visual.transformer).save_ln_outputs),
+                       "activation_policy_vision(save_ln,drop_o,keep_mlp_blocks)": list(getattr(model.visual.transformer, "last_policy", ())),
+                       "activation_policy_text(save_ln,drop_o,keep_mlp_blocks)": list(getattr(model.transformer, "last_policy", ())),
 
                        "algorithmic_gflop_per_pair": wl["gflop_per_pair"],
                        "model_flops_utilization": per_gpu_pairs * wl["gflop_per_pair"] / (peak * 1e3)},

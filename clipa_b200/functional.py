@@ -174,13 +174,18 @@ class ResidualBlockFn(torch.autograd.Function):
     Saved for backward: block input x, packed qkv, attention output, x1 (post-attention residual),
     the attention log-sum-exp and the LayerNorm statistics -- 6 activation-sized tensors; with
     `save_ln` also the two LayerNorm outputs (8 tensors; chosen by Transformer when HBM allows, it
-    removes two LayerNorm passes per block from backward).  The c_fc GEMM + activation is always
-    recomputed in backward (+11% FLOPs) instead of keeping the 4x-wide MLP activations resident.
+    removes two LayerNorm passes per block from backward).  The c_fc GEMM + activation is recomputed in
+    backward (+11% FLOPs) instead of keeping the 4x-wide MLP activations resident, unless `keep_mlp`:
+    then forward stores act(f) and act'(f) (2 x mlp_ratio more units) and backward starts at the c_proj
+    gradients -- Transformer picks it per block when HBM allows (small micro-batches of a GradCache schedule).
     """
+
+    kept_mlp_count = 0      # forwards that kept their MLP activations (tests / bench reporting)
 
     @staticmethod
     def forward(ctx, x, ln1_w, ln1_b, w_in, b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj,
-                b_proj, batch, seq, heads, causal, act, save_ln, b_proj_prev=None, skip_b_proj=False, drop_o=False):
+                b_proj, batch, seq, heads, causal, act, save_ln, b_proj_prev=None, skip_b_proj=False, drop_o=False,
+                keep_mlp=False):
         M, D = x.shape
         dev = x.device
         h1, mean1, rstd1 = ops.layernorm_fwd(x, _f32(ln1_w), _f32(ln1_b))
@@ -193,16 +198,24 @@ class ResidualBlockFn(torch.autograd.Function):
         ops.gemm(o, compute_copy(w_out), x1, bias=_bias(b_out), residual=x)
         h2, mean2, rstd2 = ops.layernorm_fwd(x1, _f32(ln2_w), _f32(ln2_b))
         g = torch.empty(M, w_fc.shape[0], dtype=_BF16, device=dev)
-        ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), act=act)
+        f = None
+        if keep_mlp:        # (grad mode is always off inside Function.forward: the caller decides, Transformer._activation_policy)
+            ResidualBlockFn.kept_mlp_count += 1
+            f = torch.empty_like(g)                        # act'(c_fc(h2)), the same kernel backward would run
+            ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), aux=f, act=act,
+                     aux_is_derivative=True)
+        else:
+            ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), act=act)
         if not save_ln:
             h2 = None
         y = torch.empty(M, D, dtype=_BF16, device=dev)
         ops.gemm(g, compute_copy(w_proj), y, bias=_bias(b_proj), residual=x1)
-        del g
+        if f is None:
+            g = None
         if drop_o:
             o = None        # recomputed from qkv in backward (Transformer._activation_policy: HBM is tight)
         ctx.save_for_backward(x, qkv, o, lse, x1, mean1, rstd1, mean2, rstd2, ln1_w, ln1_b, w_in,
-                              b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj, h1, h2)
+                              b_in, w_out, b_out, ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj, h1, h2, g, f)
         ctx.meta = (batch, seq, heads, causal, act)
         # Bias gradients that are column sums of a LayerNorm-backward OUTPUT are produced by that kernel:
         # d(out_proj.bias) = colsum(dx1) here; d(c_proj.bias) of the PREVIOUS block = colsum(dx), the gradient this
@@ -215,7 +228,7 @@ class ResidualBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         (x, qkv, o, lse, x1, mean1, rstd1, mean2, rstd2, ln1_w, ln1_b, w_in, b_in, w_out, b_out,
-         ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj, h1, h2) = ctx.saved_tensors
+         ln2_w, ln2_b, w_fc, b_fc, w_proj, b_proj, h1, h2, g, f) = ctx.saved_tensors
         batch, seq, heads, causal, act = ctx.meta
         b_prev = ctx.prev_bias
         M, D = x.shape
@@ -225,10 +238,11 @@ class ResidualBlockFn(torch.autograd.Function):
         # ---- MLP: (recompute h2,) f = c_fc(h2), g = act(f)
         if h2 is None:
             h2, _, _ = ops.layernorm_fwd(x1, _f32(ln2_w), _f32(ln2_b), save_stats=False)
-        f = torch.empty(M, H4, dtype=_BF16, device=dev)      # receives act'(c_fc(h2)): the dgrad GEMM below only multiplies
-        g = torch.empty(M, H4, dtype=_BF16, device=dev)
-        ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), aux=f, act=act,
-                 aux_is_derivative=True)
+        if f is None:                                            # not kept by forward: recompute
+            f = torch.empty(M, H4, dtype=_BF16, device=dev)      # receives act'(c_fc(h2)): the dgrad GEMM below only multiplies
+            g = torch.empty(M, H4, dtype=_BF16, device=dev)
+            ops.gemm(h2, compute_copy(w_fc), g, epilogue=EPI_BIAS_ACT, bias=_bias(b_fc), aux=f, act=act,
+                     aux_is_derivative=True)
         d_w_proj = _wgrad(dy, g, w_proj)
         d_b_proj = None if ctx.skip_b_proj else _bgrad(dy, b_proj)     # else: the next block's LayerNorm backward did it
         del g
@@ -278,7 +292,7 @@ class ResidualBlockFn(torch.autograd.Function):
         g_ln2 = (None, None) if direct2 else (d_ln2_w.to(ln2_w.dtype), d_ln2_b.to(ln2_b.dtype))
         return (dx, g_ln1[0], g_ln1[1], d_w_in, d_b_in, d_w_out, d_b_out,
                 g_ln2[0], g_ln2[1], d_w_fc, d_b_fc, d_w_proj, d_b_proj,
-                None, None, None, None, None, None, d_b_prev, None, None)
+                None, None, None, None, None, None, d_b_prev, None, None, None)
 
 
 class ClipLossFn(torch.autograd.Function):

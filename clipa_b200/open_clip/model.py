@@ -127,7 +127,10 @@ def _reserve_for_later(model, text_tower, image, text) -> None:
     head = int(getattr(model, "head_reserve_bytes", 1 << 30))
     vt = model.visual.transformer
     gh, gw = model.visual.grid_size
-    text_tower.other_need_bytes = vt.base_need_bytes(image.shape[0] * (gh * gw + 1)) + head
+    rows = image.shape[0] * (gh * gw + 1)
+    text_tower.other_need_bytes = vt.base_need_bytes(rows) + head
+    # the (small) text tower keeps its MLP activations only if the vision tower can still keep all of its own
+    text_tower.keep_reserve_bytes = vt.full_need_bytes(rows) - vt.base_need_bytes(rows)
     vt.other_need_bytes = head
 
 

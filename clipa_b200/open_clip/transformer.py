@@ -102,7 +102,7 @@ class ResidualAttentionBlock(nn.Module):
 
     def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool, save_ln: bool = False,
                 prev_proj_bias: Optional[torch.Tensor] = None, proj_bias_grad_by_next: bool = False,
-                recompute_attn_out: bool = False):
+                recompute_attn_out: bool = False, keep_mlp: bool = False):
         """x: [batch*seq, d_model] bf16, sample-major rows.  prev_proj_bias / proj_bias_grad_by_next: the c_proj bias
         gradient of a block is the column sum of the gradient the NEXT block's LayerNorm backward writes, so the next
         block produces it (see functional.ResidualBlockFn)."""
@@ -111,7 +111,7 @@ class ResidualAttentionBlock(nn.Module):
             self.attn.out_proj.weight, self.attn.out_proj.bias, self.ln_2.weight, self.ln_2.bias,
             self.mlp.c_fc.weight, self.mlp.c_fc.bias, self.mlp.c_proj.weight, self.mlp.c_proj.bias,
             batch, seq, self.n_head, causal, self.act, save_ln, prev_proj_bias, proj_bias_grad_by_next,
-            recompute_attn_out)
+            recompute_attn_out, keep_mlp)
 
 
 class _GradReady:
@@ -148,20 +148,32 @@ class Transformer(nn.Module):
     #   6 units / block  LayerNorm outputs recomputed in backward          default
     #   5 units / block  attention output o recomputed too (one extra attention forward per block)
     #                    when even 6 units + 3 GiB would not fit (ViT-H/14 at 8192 pairs per GPU: 2 GiB were left)
+    #   + 2 x mlp_ratio units for every block that also keeps act(f) and act'(f) of its MLP (no c_fc recompute GEMM in
+    #                    backward: -10 % of a block's GEMM FLOPs); as many of the LAST blocks as fit next to the
+    #                    8-unit level with an 8 GiB margin -- all of them at the 2048-pair micro-batches of a
+    #                    GradCache schedule, a handful at 4096 pairs per GPU
     # `other_need_bytes` = what still has to fit AFTER this tower's forward (the other tower, the contrastive head):
-    # set by CLIP.forward.  save_ln_outputs / recompute_attn_out = True / False force a level.
+    # set by CLIP.forward.  save_ln_outputs / recompute_attn_out = True / False force a level; keep_mlp_blocks =
+    # an int forces the number of MLP-keeping blocks.
     save_ln_outputs = "auto"
     recompute_attn_out = "auto"
+    keep_mlp_blocks = "auto"
     other_need_bytes = 0
+    keep_reserve_bytes = 0     # extra room the MLP-keeping decision leaves for the tower that runs afterwards
 
     def base_need_bytes(self, rows: int) -> int:
         """Bytes this tower keeps for backward at the default level (+ backward transients), for `rows` tokens."""
         return (6 * self.layers + 10) * rows * self.width * 2
 
+    def full_need_bytes(self, rows: int) -> int:
+        """Same at the richest level: LayerNorm outputs and the MLP activations of every block kept."""
+        mlp_units = 2 * self.resblocks[0].mlp.c_fc.out_features / self.width
+        return int(((8 + mlp_units) * self.layers + 10) * rows * self.width * 2)
+
     def _activation_policy(self, x: torch.Tensor):
-        """-> (save_ln, drop_o)"""
+        """-> (save_ln, drop_o, number of trailing blocks that keep their MLP activations)"""
         if not torch.is_grad_enabled() or not x.is_cuda:
-            return False, False
+            return False, False, 0
         unit = x.numel() * x.element_size()
         free, _ = torch.cuda.mem_get_info(x.device)
         free += torch.cuda.memory_reserved(x.device) - torch.cuda.memory_allocated(x.device)
@@ -174,7 +186,14 @@ class Transformer(nn.Module):
             drop_o = (not save_ln) and (6 * self.layers + 10) * unit + (3 << 30) > free
         else:
             drop_o = bool(self.recompute_attn_out)
-        return save_ln, drop_o
+        if self.keep_mlp_blocks == "auto":
+            mlp_units = 2 * self.resblocks[0].mlp.c_fc.out_features / self.width
+            spare = free - (8 * self.layers + 10) * unit - (8 << 30) - self.keep_reserve_bytes
+            keep = int(spare // (mlp_units * unit)) if (save_ln and spare > 0) else 0
+            keep = max(0, min(self.layers, keep))
+        else:
+            keep = max(0, min(self.layers, int(self.keep_mlp_blocks)))
+        return save_ln, drop_o, keep
 
     def _decide_save_ln(self, x: torch.Tensor) -> bool:
         return self._activation_policy(x)[0]
@@ -185,14 +204,16 @@ class Transformer(nn.Module):
     grad_bucket_blocks = 4
 
     def forward(self, x: torch.Tensor, batch: int, seq: int, causal: bool = False):
-        save_ln, drop_o = self._activation_policy(x)
+        save_ln, drop_o, keep = self._activation_policy(x)
+        if torch.is_grad_enabled():
+            self.last_policy = (save_ln, drop_o, keep)      # reported by bench.py
         cb = self.grad_ready_callback if torch.is_grad_enabled() else None
         n_blocks = len(self.resblocks)
         for i, r in enumerate(self.resblocks):
             if cb is not None and x.requires_grad and i % self.grad_bucket_blocks == 0:
                 x.register_hook(_GradReady(cb, self, i))
             prev = self.resblocks[i - 1].mlp.c_proj.bias if i > 0 else None
-            x = r(x, batch, seq, causal, save_ln, prev, i + 1 < n_blocks, drop_o)
+            x = r(x, batch, seq, causal, save_ln, prev, i + 1 < n_blocks, drop_o, i >= n_blocks - keep)
         return x
 
 

@@ -311,19 +311,23 @@ def test_patch_dropout_runs_on_device(dev):
 
 
 def test_activation_policy_save_ln_equals_recompute(dev):
-    """The three activation-memory levels (keep LayerNorm outputs / recompute them / also recompute the attention
-    output) are the same math."""
+    """The activation-memory levels (keep LayerNorm outputs / recompute them / also recompute the attention output /
+    keep the MLP activations of all or of the last block) are the same math."""
     from clipa_b200.open_clip.transformer import Transformer
     meta, _ = load_golden("tiny-gap-h80", "fp32")
     grads = []
-    old = (Transformer.save_ln_outputs, Transformer.recompute_attn_out)
+    old = (Transformer.save_ln_outputs, Transformer.recompute_attn_out, Transformer.keep_mlp_blocks)
     try:
-        for save_ln, drop_o in ((True, False), (False, False), (False, True)):
-            Transformer.save_ln_outputs, Transformer.recompute_attn_out = save_ln, drop_o
+        for save_ln, drop_o, keep in ((True, False, 0), (False, False, 0), (False, True, 0), (True, False, 99), (False, False, 1)):
+            Transformer.save_ln_outputs, Transformer.recompute_attn_out, Transformer.keep_mlp_blocks = save_ln, drop_o, keep
+            from clipa_b200.functional import ResidualBlockFn
+            kept0 = ResidualBlockFn.kept_mlp_count
             model, _, _, loss = run_ours(meta, "amp_bf16", dev)
+            n_blocks = len(model.visual.transformer.resblocks) + len(model.transformer.resblocks)
+            assert ResidualBlockFn.kept_mlp_count - kept0 == (0 if keep == 0 else (n_blocks if keep == 99 else 2))
             grads.append((loss.item(), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}))
     finally:
-        Transformer.save_ln_outputs, Transformer.recompute_attn_out = old
+        Transformer.save_ln_outputs, Transformer.recompute_attn_out, Transformer.keep_mlp_blocks = old
     for l1, g1 in grads[1:]:
         assert grads[0][0] == l1
         for n in grads[0][1]:
