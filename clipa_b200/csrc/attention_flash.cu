@@ -1123,6 +1123,7 @@ long long attention_bwd_flash_workspace(int batch, int L, int H, int hd) {
   int T, Rt, npad, G;
   flash_tiling(L, kFlMaxRowsBwd, T, Rt, npad, G);
   if (T <= 1) return 0;
+  if (flash_dq_tmem_enabled() && T * hd + 2 * npad + 2 * hd <= 512) return 0;   // dQ tiles stay in tensor memory
   long long grid = num_sms();
   if (grid > (long long)batch * H) grid = (long long)batch * H;
   return grid * T * Rt * hd * 4;

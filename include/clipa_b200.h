@@ -117,7 +117,8 @@ int clipa_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, i
 /* Backward of the same call site (autograd of F.multi_head_attention_forward's SDPA): dqkv bf16
  * [batch*L, 3*D] receives dQ | dK | dV.  Sequences longer than one tile (L > 128, the 224/336-px
  * fine-tune stages) sum the dQ partials of their key tiles through a caller-provided fp32
- * workspace of clipa_attention_bwd_workspace() bytes (0 for one-tile shapes: pass NULL, 0). */
+ * workspace of clipa_attention_bwd_workspace() bytes (0 for one-tile shapes and for shapes whose
+ * dQ tiles all stay in tensor memory, e.g. L = 257 at head_dim 64: pass NULL, 0). */
 int64_t clipa_attention_bwd_workspace(int32_t batch, int32_t L, int32_t heads, int32_t head_dim);
 int clipa_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                         void* dqkv, void* workspace, int64_t workspace_bytes, int32_t batch, int32_t L,

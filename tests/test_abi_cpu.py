@@ -65,7 +65,9 @@ def test_null_and_bad_arguments_are_rejected_with_messages(lib):
     assert lib.clipa_attention_fwd(None, None, None, 1, 1, 1, 64, 0, None) == -1
     assert lib.clipa_clip_lse(None, None, 8, 8, 64, 1.0, None, 0, None, None, None, None) == -1
     assert lib.clipa_attention_bwd(None, None, None, None, None, None, 0, 1, 1, 1, 64, 0, None) == -1
-    assert lib.clipa_attention_bwd_workspace(2, 257, 4, 64) >= 2 * 4 * 258 * 64 * 4   # 3 tiles of 86 rows, fp32 dQ partials
+    assert lib.clipa_attention_bwd_workspace(2, 577, 4, 64) >= 2 * 4 * 577 * 64 * 4   # 7 tiles of 83 rows, fp32 dQ partials
+    assert lib.clipa_attention_bwd_workspace(2, 257, 4, 80) >= 2 * 4 * 257 * 80 * 4
+    assert lib.clipa_attention_bwd_workspace(2, 257, 4, 64) == 0                      # 3 dQ tiles stay in tensor memory
     assert lib.clipa_attention_bwd_workspace(2, 82, 4, 64) == 0
     assert lib.clipa_clip_lse_workspace(4096, 32768) > 0
     assert lib.clipa_launch_count() == 0   # nothing was launched by the rejected calls
