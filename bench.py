@@ -9,8 +9,10 @@ ViT-L/14, global batch 32k, on 1/2/4/8 B200).
 A "step" is one full optimizer step at the named global batch: H2D/preprocess (e2e only) ->
 towers forward -> all-gather -> fused contrastive head -> backward -> gradient all-reduce ->
 AdamW -> logit-scale clamp.  Global batch is FIXED as N grows ("strong" scaling): each rank
-processes global/N pairs in micro-batches of <= --micro-batch (GradCache schedule when more than
-one micro-batch is needed, as in the reference's accum_freq path).
+processes global/N pairs -- as one plain forward/backward when that fits 180 GB (4096 pairs of the
+headline model: N = 8), otherwise in chunks with the reference's GradCache schedule (accum_freq
+path); the chunk size (--micro-batch, default per workload) is the one at which every block can keep
+its MLP activations, so backward skips the c_fc recompute GEMM.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
