@@ -35,7 +35,24 @@
 
 namespace clipa {
 
+// Warp roles.  CLIPA_FLASH_ROLES = 0: warp 0 = TMA, warp 1 = MMA issuer, warps 2-9 = workers (TMEM lane quarter
+// = warp & 3): the two producer warps share SM sub-partitions 0 and 1 with the quarter-0 / quarter-1 workers.
+// = 1: 12 warps, workers 0-7, TMA = warp 10, MMA = warp 11 (sub-partitions 2 and 3: with 86-row tiles quarter 3 has
+// no rows, so the issuer gets a scheduler of its own); warps 8, 9 exit at once.
+#ifndef CLIPA_FLASH_ROLES
+#define CLIPA_FLASH_ROLES 0
+#endif
+#if CLIPA_FLASH_ROLES == 1
+constexpr int kFlThreads = 384;
+constexpr int kFlTmaWarp = 10, kFlMmaWarp = 11;
+__device__ __forceinline__ bool fl_is_worker(int warp) { return warp < 8; }
+__device__ __forceinline__ int fl_half(int warp) { return warp >> 2; }
+#else
 constexpr int kFlThreads = 320;
+constexpr int kFlTmaWarp = 0, kFlMmaWarp = 1;
+__device__ __forceinline__ bool fl_is_worker(int warp) { return warp >= 2; }
+__device__ __forceinline__ int fl_half(int warp) { return (warp - 2) >> 2; }
+#endif
 constexpr int kFlMaxRowsFwd = 128;  // forward: rows (queries / keys) per tile (full 128-row operand tiles)
 constexpr int kFlMaxRowsBwd = 96;   // backward: 96-row operand tiles (shared-memory budget)
 
@@ -204,7 +221,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
     n = (nh / H) * G;
   };
 
-  if (warp == 0) {
+  if (warp == kFlTmaWarp) {
     if (lane == 0) {
       // step cursors (item, key tile) advance incrementally: no integer division per step
       StepCursor ck, cv;
@@ -241,7 +258,7 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
         load_v(k);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kFlMmaWarp) {
     const IssueMode im = issue_mode(lane);
     if (im.in_loop) {
       const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.npad, false, false);
@@ -280,9 +297,9 @@ attn_fwd_flash_kernel(const __grid_constant__ CUtensorMap tmap_main, const __gri
         if (k + 2 < K) issue_s(k + 2);                // S buffer s is free: p_full(k) has been seen
       }
     }
-  } else {
+  } else if (fl_is_worker(warp)) {
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;     // column half of the score row / of the output row
+    const int half = fl_half(warp);       // column half of the score row / of the output row
     const int row = q * 32 + lane;
     const bool warp_active = q * 32 < Rt;  // warp-uniform and equal for the two halves of a quarter
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -717,7 +734,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
   auto pds_buf = [&](int k) -> int { return PIPE ? (k & 1) : 0; };
   auto pds_par = [&](int k) -> uint32_t { return PIPE ? ((k >> 1) & 1) : (k & 1); };
 
-  if (warp == 0) {
+  if (warp == kFlTmaWarp) {
     if (lane == 0) {
       BwdCursor c;
       c.init(T);
@@ -743,7 +760,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
         if (c.advance() && c.it < n_local) decode(c);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kFlMmaWarp) {
     const IssueMode im = issue_mode(lane);
     if (im.in_loop) {
       const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)p.npad, false, false);   // A K-major, B K-major
@@ -821,9 +838,9 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tq_main, const __grid_
         if (!PIPE && k + 1 < K) issue_scores(k + 1);
       }
     }
-  } else {
+  } else if (fl_is_worker(warp)) {
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = fl_half(warp);
     const int row = q * 32 + lane;          // query index (scores stage, dQ rows) / key index (dK, dV rows)
     const bool warp_writes = q * 32 < p.npad;
     const bool warp_stores = q * 32 < Rt;
