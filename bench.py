@@ -47,6 +47,12 @@ WORKLOADS = {
     "vitb32_i36_t16_gb256": dict(model="ViT-B-32-CL16", image=192, pos="sin_cos_2d", global_batch=256,
                                  gflop_per_pair=23.16, baseline_config="configs[0] shape, batch 256", micro=(256, 128)),
 }
+def pick_micro_batch(wl: dict, per_gpu_batch: int) -> int:
+    """The whole per-GPU batch when it runs as one plain forward/backward, else the workload's GradCache chunk size."""
+    plain, chunk = wl["micro"]
+    return per_gpu_batch if per_gpu_batch <= plain else chunk
+
+
 METRIC = "image-text pairs/sec at ViT-L/14, global batch 32k, 1/2/4/8 B200"
 
 
@@ -280,8 +286,7 @@ def main():
     _T.save_ln_outputs = {"auto": "auto", "on": True, "off": False}[args.save_ln]
     _T.keep_mlp_blocks = "auto" if args.keep_mlp == "auto" else int(args.keep_mlp)
     if args.micro_batch <= 0:
-        plain, chunk = wl["micro"]
-        args.micro_batch = plain if bl <= plain else chunk
+        args.micro_batch = pick_micro_batch(wl, bl)
     model.train()
     trainer = TrainStep(model, rank=rank, world_size=world, micro_batch=args.micro_batch,
                         overlap_grad_allreduce=os.environ.get("CLIPA_OVERLAP", "0") == "1")

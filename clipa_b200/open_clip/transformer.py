@@ -125,6 +125,28 @@ class _GradReady:
         return None
 
 
+def activation_levels(free: int, unit: int, layers: int, mlp_units: float, keep_reserve: int = 0,
+                      save_ln="auto", drop_o="auto", keep_mlp="auto"):
+    """Activation-memory level of a tower from the HBM that is free for it (bytes, already minus what the rest of the
+    step still needs), `unit` = bytes of one [tokens, width] bf16 tensor.  -> (save LayerNorm outputs, recompute the
+    attention output, number of trailing blocks that keep their MLP activations).  "auto" entries are decided here,
+    anything else is forced (see the comment block in Transformer)."""
+    if save_ln == "auto":
+        save_ln = (8 * layers + 10) * unit + (6 << 30) < free
+    else:
+        save_ln = bool(save_ln)
+    if drop_o == "auto":
+        drop_o = (not save_ln) and (6 * layers + 10) * unit + (3 << 30) > free
+    else:
+        drop_o = bool(drop_o)
+    if keep_mlp == "auto":
+        spare = free - (8 * layers + 10) * unit - (8 << 30) - keep_reserve
+        keep = int(spare // (mlp_units * unit)) if (save_ln and spare > 0) else 0
+    else:
+        keep = int(keep_mlp)
+    return save_ln, drop_o, max(0, min(layers, keep))
+
+
 class Transformer(nn.Module):
     """open_clip/transformer.py:294-326.  `grad_checkpointing` is accepted for API parity; the block
     function already recomputes its MLP activations, so the flag does not change the math."""
@@ -174,26 +196,11 @@ class Transformer(nn.Module):
         """-> (save_ln, drop_o, number of trailing blocks that keep their MLP activations)"""
         if not torch.is_grad_enabled() or not x.is_cuda:
             return False, False, 0
-        unit = x.numel() * x.element_size()
         free, _ = torch.cuda.mem_get_info(x.device)
         free += torch.cuda.memory_reserved(x.device) - torch.cuda.memory_allocated(x.device)
-        free -= self.other_need_bytes
-        if self.save_ln_outputs == "auto":
-            save_ln = (8 * self.layers + 10) * unit + (6 << 30) < free
-        else:
-            save_ln = bool(self.save_ln_outputs)
-        if self.recompute_attn_out == "auto":
-            drop_o = (not save_ln) and (6 * self.layers + 10) * unit + (3 << 30) > free
-        else:
-            drop_o = bool(self.recompute_attn_out)
-        if self.keep_mlp_blocks == "auto":
-            mlp_units = 2 * self.resblocks[0].mlp.c_fc.out_features / self.width
-            spare = free - (8 * self.layers + 10) * unit - (8 << 30) - self.keep_reserve_bytes
-            keep = int(spare // (mlp_units * unit)) if (save_ln and spare > 0) else 0
-            keep = max(0, min(self.layers, keep))
-        else:
-            keep = max(0, min(self.layers, int(self.keep_mlp_blocks)))
-        return save_ln, drop_o, keep
+        return activation_levels(free - self.other_need_bytes, x.numel() * x.element_size(), self.layers,
+                                 2 * self.resblocks[0].mlp.c_fc.out_features / self.width, self.keep_reserve_bytes,
+                                 self.save_ln_outputs, self.recompute_attn_out, self.keep_mlp_blocks)
 
     def _decide_save_ln(self, x: torch.Tensor) -> bool:
         return self._activation_policy(x)[0]

@@ -379,3 +379,44 @@ def test_train_step_optimizer_state_dict_is_adamw_compatible():
         assert torch.equal(mine["state"][k]["exp_avg_sq"], st["exp_avg_sq"])
         assert float(mine["state"][k]["step"]) == float(st["step"])
     ref.load_state_dict(mine)                       # and back into the reference optimizer
+
+
+def test_activation_levels_follow_the_free_hbm():
+    """Transformer's activation-memory policy as plain arithmetic: ViT-L/14 vision tower,
+    82 tokens; one unit = one [pairs*82, 1024] bf16 tensor."""
+    from clipa_b200.open_clip.transformer import activation_levels
+    GiB = 1 << 30
+    L, r2 = 24, 8.0
+    unit4096 = 4096 * 82 * 1024 * 2
+    unit2048 = unit4096 // 2
+    # 4096 pairs, ~165 GB free for the tower: LayerNorm outputs kept, a handful of blocks keep their MLP activations
+    save_ln, drop_o, keep = activation_levels(165 * GiB, unit4096, L, r2)
+    assert save_ln and not drop_o and 0 < keep < 8
+    # 2048 pairs with the same room: every block keeps them
+    assert activation_levels(165 * GiB, unit2048, L, r2) == (True, False, L)
+    # tight: below the 8-unit level -> recompute the LayerNorm outputs, keep nothing; tighter still -> also drop O
+    need6 = (6 * L + 10) * unit4096
+    assert activation_levels(need6 + 4 * GiB, unit4096, L, r2) == (False, False, 0)
+    assert activation_levels(need6 + 1 * GiB, unit4096, L, r2) == (False, True, 0)
+    # the reservation for the tower that runs afterwards only limits the MLP-keeping decision
+    full = activation_levels(165 * GiB, unit2048, L, r2, keep_reserve=0)[2]
+    held = activation_levels(165 * GiB, unit2048, L, r2, keep_reserve=100 * GiB)[2]
+    assert full == L and held < L
+    # forced levels override the arithmetic and are clamped to the depth of the tower
+    assert activation_levels(0, unit4096, L, r2, save_ln=True, drop_o=False, keep_mlp=99) == (True, False, L)
+    assert activation_levels(1 << 50, unit4096, L, r2, save_ln=False, drop_o=True, keep_mlp=0) == (False, True, 0)
+
+
+def test_bench_micro_batch_choice():
+    """bench.py: one plain step when the per-GPU batch fits, else the workload's GradCache chunk size."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("clipa_bench", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    wl = bench.WORKLOADS["vitl14_i81_t16_gb32k"]
+    assert [bench.pick_micro_batch(wl, wl["global_batch"] // n) for n in (1, 2, 4, 8)] == [2048, 2048, 2048, 4096]
+    for name, w in bench.WORKLOADS.items():
+        plain, chunk = w["micro"]
+        assert chunk <= plain and w["global_batch"] % chunk == 0, name
+        assert (w["global_batch"] // 8) % bench.pick_micro_batch(w, w["global_batch"] // 8) == 0, name
